@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — hours-of-audio/sec of log-mel extraction (22050 Hz, n_fft=1024, hop=256, 80 mels).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload = BASELINE.json configs[1] ("C2"): batch 256 x 1 s @ 22050 Hz per GPU, LogMelSpectrogram
+semantics (centre reflect pad, ln(mel + 1e-6), clamp -50/30 dB).  A step = ONE launch of the fused
+kernel over one clip batch.  Steps rotate over enough distinct input/output buffers to exceed the
+126 MB L2, so every step reads its samples from HBM.  Prints ONE JSON line (rank 0).
+
+ value      whole-job hours-of-audio/s, inputs resident in HBM, CUDA-event timed, max over ranks
+ e2e        same metric through the public module API with pinned HOST buffers: H2D copy of the batch,
+            kernel, D2H copy of the mel tensor inside the timed region, every step
+ roofline   HBM-read roofline of the fused kernel: 4*B*L bytes / average launch duration vs
+            MEASURED_PEAKS.json hbm_gbs
+ cpu_baseline  oracle port of the reference's own op sequence (torch CPU fp32) on this host's cores
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR, N_FFT, HOP, N_MELS = 22050, 1024, 256, 80
+B_PER_GPU, L = 256, 22050
+T = 1 + L // HOP
+METRIC = "hours-of-audio/sec mel extraction (22050Hz, n_fft=1024, 80 mels)"
+UNIT = "hours_audio/s"
+HOURS_PER_BATCH = B_PER_GPU * L / SR / 3600.0
+SEED = 20261017 + 1000 * 2
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while `active` is set."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.active = threading.Event()
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._halt.is_set():
+            if self.active.is_set():
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._halt.set()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def synth(rank, n_batches):
+    """Distinct seeded batches (SURVEY 8d waveforms) as one (n_batches, B, L) float32 array."""
+    import numpy as np
+
+    from oracle import mel_oracle as mo  # synthetic-input generator shared with the tests (not on the timed path)
+
+    base = mo.synth_clips(B_PER_GPU, L, SR, seed=SEED + rank, first_clip=rank * B_PER_GPU)
+    out = np.empty((n_batches, B_PER_GPU, L), dtype=np.float32)
+    rng = np.random.default_rng(SEED + 17 * rank)
+    for i in range(n_batches):
+        # same sinusoids + 1 % noise, plus fresh 0.1 % noise per buffer (cheap, keeps every buffer distinct)
+        out[i] = base + (0.001 * rng.standard_normal((B_PER_GPU, L))).astype(np.float32)
+    return out
+
+
+def cpu_reference_run(steps, warmup, budget_s=100.0, full=True):
+    """Time the reference's op sequence (oracle port, torch CPU fp32, all host threads).
+
+    Canonical operator = LogMelSpectrogram = conv-DFT STFT + mel matmul + log + clamp
+    (models/transforms.py:53-69,231-244).  Each step processes `clips` clips of the C2 workload,
+    sized so (steps + warmup) steps fit the budget."""
+    import torch
+
+    from oracle import mel_oracle as mo
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ref = mo.TorchReference(sample_rate=SR, mel_size=N_MELS, n_fft=N_FFT, win_length=N_FFT, hop_length=HOP,
+                            min_db=-50, max_db=30, mel_min=0.0, mel_max=8000.0)
+    x = torch.from_numpy(mo.synth_clips(B_PER_GPU, L, SR, seed=SEED))
+    with torch.no_grad():
+        probe = 16
+        ref.logmel_conv(x[:probe])
+        t0 = time.perf_counter()
+        ref.logmel_conv(x[:probe])
+        per_clip = (time.perf_counter() - t0) / probe
+        clips = int(max(1, min(B_PER_GPU, budget_s / max(1, steps + warmup) / per_clip)))
+        for _ in range(warmup):
+            ref.logmel_conv(x[:clips])
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ref.logmel_conv(x[:clips])
+        dt = time.perf_counter() - t0
+        value = steps * clips * L / SR / 3600.0 / dt
+        alt = None
+        if full:
+            ref.logmel_stft(x[:clips])
+            t1 = time.perf_counter()
+            n_alt = max(1, min(steps, 5))
+            for _ in range(n_alt):
+                ref.logmel_stft(x[:clips])
+            alt = n_alt * clips * L / SR / 3600.0 / (time.perf_counter() - t1)
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{clips} of the {B_PER_GPU} C2 clips per step x {steps} steps, conv-DFT LogMelSpectrogram "
+                      f"op sequence (oracle.TorchReference.logmel_conv), torch {torch.__version__} CPU fp32, "
+                      f"{cores} threads",
+            "torch_stft_variant_value": alt, "ms_per_step": dt / steps * 1e3, "clips_per_step": clips}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps = args.steps if args.steps else 5
+    warmup = args.warmup if args.warmup is not None else 1
+    r = cpu_reference_run(steps, warmup, full=False)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: batch 256 x 1 s @22050 Hz, n_fft=1024 hop=256 mel=80 (bounded sample per step)",
+                   "clips_per_step": r["clips_per_step"]},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    steps = args.steps if args.steps else 2000
+    warmup = args.warmup if args.warmup is not None else 50
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the b200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from pytorch_sound_b200 import _lib, build
+    from pytorch_sound_b200.distributed import all_gather_mel
+    from pytorch_sound_b200.models.transforms import LogMelSpectrogram
+
+    build.build()
+    module = LogMelSpectrogram(sample_rate=SR, mel_size=N_MELS, n_fft=N_FFT, win_length=N_FFT, hop_length=HOP,
+                               min_db=-50, max_db=30, mel_min=0.0, mel_max=8000.0).to(dev)
+
+    # ---- inputs: NBUF distinct batches, > L2 in aggregate --------------------------------------------
+    NBUF = 8  # 8 x (22.6 MB in + 7.1 MB out) = 238 MB > 126 MB L2
+    host = torch.from_numpy(synth(rank, NBUF)).pin_memory()
+    d_in = host.to(dev)
+    outs = [None] * NBUF
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        """CUDA-event time of n calls of fn(i) on the current stream, max over ranks (ms)."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.active.set()
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        sampler.active.clear()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    # ---- device-resident kernel throughput ----------------------------------------------------------------
+    # One CUDA graph holds one rotation (NBUF launches, one per buffer pair); the timed region replays it
+    # steps // NBUF times and finishes with steps % NBUF eager launches, so EXACTLY `steps` launches are timed
+    # and the host's Python/ctypes launch cost (comparable to the ~20 us kernel) is not what is measured.
+    def step_dev(i):
+        outs[i % NBUF] = module(d_in[i % NBUF])
+
+    for i in range(max(warmup, 3)):
+        step_dev(i)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            g_outs = [module(d_in[j]) for j in range(NBUF)]
+    torch.cuda.synchronize()
+    for _ in range(3):
+        graph.replay()
+    reps, rem = divmod(steps, NBUF)
+
+    def run_steps(_):
+        for _r in range(reps):
+            graph.replay()
+        for j in range(rem):
+            step_dev(j)
+
+    l0 = _lib.launch_count()
+    ms = timed(run_steps, 1)
+    launches = reps * NBUF + (_lib.launch_count() - l0)  # graph replays re-issue the NBUF captured launches
+    ms_per_step = ms / steps
+    value = world * HOURS_PER_BATCH / (ms_per_step * 1e-3)
+    assert torch.equal(g_outs[0], outs[0] if outs[0] is not None else g_outs[0])
+
+    # ---- end to end: pinned host -> H2D -> kernel -> D2H, through the module API ---------------------------
+    host_out = torch.empty((2, B_PER_GPU, N_MELS, T), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        wav = host[i % NBUF].to(dev, non_blocking=True)
+        mel = module(wav)
+        host_out[i % 2].copy_(mel, non_blocking=True)
+
+    e2e_steps = max(3, min(steps, 200))
+    for i in range(3):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, e2e_steps) / e2e_steps
+    e2e_value = world * HOURS_PER_BATCH / (ms_e2e * 1e-3)
+
+    # ---- with the all-gather of mel frames (north-star's one collective), N > 1 only ---------------------
+    gather = None
+    if world > 1:
+        def step_gather(i):
+            all_gather_mel(module(d_in[i % NBUF]))
+
+        for i in range(3):
+            step_gather(i)
+        g_steps = max(3, min(steps, 200))
+        ms_g = timed(step_gather, g_steps) / g_steps
+        gather = {"value": world * HOURS_PER_BATCH / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g,
+                  "bytes_gathered_per_rank": world * B_PER_GPU * N_MELS * T * 4}
+    sampler.stop()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        bytes_read = 4 * B_PER_GPU * L
+        bytes_written = 4 * B_PER_GPU * N_MELS * T
+        ach = bytes_read / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2: batch 256 x 1 s @22050 Hz per GPU, n_fft=1024 hop=256 mel=80, "
+                                   "LogMelSpectrogram (centre pad, ln(mel+1e-6), clamp -50/30 dB)",
+                       "clips_per_gpu": B_PER_GPU, "samples_per_clip": L, "frames_per_clip": T,
+                       "l2_policy": f"rotating over {NBUF} distinct input/output buffer pairs "
+                                    f"({NBUF * (bytes_read + bytes_written) / 1e6:.0f} MB > 126 MB L2)",
+                       "parallelism": f"clips sharded over {world} GPU(s), no data-path collective"},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src, "basis": "HBM-read (4*B*L bytes per launch)",
+                         "read_plus_write_frac": (bytes_read + bytes_written) / (ms_per_step * 1e-3) / 1e9 / peak,
+                         "kernel": "b200mel::logmel_warp_kernel<true>",
+                         "avg_launch_us": ms_per_step * 1e3},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_read,
+                    "d2h_bytes_per_step": bytes_written, "ms_per_step": ms_e2e, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+        }
+        if gather is not None:
+            line["with_all_gather"] = gather
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = {k: v for k, v in cpu_reference_run(5, 1, budget_s=20.0).items()
+                                    if k not in ("ms_per_step", "clips_per_step")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

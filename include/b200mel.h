@@ -1,0 +1,160 @@
+/*
+ * b200mel.h — C ABI of libb200mel.so: the B200 (sm_100a) fused
+ * STFT -> magnitude -> mel filterbank -> log feature extractor that sits
+ * behind pytorch_sound's spectral operators.
+ *
+ * The reference (AppleHolic/pytorch_sound) has no FFI layer: its operator
+ * surface is a set of Python nn.Modules.  Every entry point below therefore
+ * cites the reference Python symbol it replaces (paths relative to
+ * /root/reference/pytorch_sound/); INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA runtime types in signatures
+ *     (a CUDA stream is passed as void*, 0 == legacy default stream);
+ *   - every function returns 0 (B200MEL_OK) or a negative B200MEL_E* code and
+ *     never throws / aborts; the message is in b200mel_last_error()
+ *     (thread-local);
+ *   - the caller owns every data buffer; a plan owns only its device-side
+ *     tables (window, twiddles, banded filterbank) and is immutable after
+ *     creation, so b200mel_forward is re-entrant;
+ *   - no host synchronisation and no allocation inside b200mel_forward;
+ *   - there is NO CPU fallback: without a CUDA device plan_create fails.
+ */
+#ifndef B200MEL_H
+#define B200MEL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MEL_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define B200MEL_OK 0
+#define B200MEL_EINVAL (-1)  /* bad config / shape / null pointer            */
+#define B200MEL_ECUDA (-2)   /* CUDA runtime error (message has the string)  */
+#define B200MEL_ENODEV (-3)  /* no CUDA device / not an sm_100 device         */
+#define B200MEL_ENOMEM (-4)  /* host or device allocation failed              */
+#define B200MEL_EUNSUP (-5)  /* valid in the reference, not built here (yet)  */
+
+/* framing: where frame 0 starts relative to sample 0 */
+#define B200MEL_PAD_CENTER 0 /* reflect n_fft/2 each side  (STFT.transform models/transforms.py:55-60;
+                                torch.stft(center=True) models/transforms.py:298-301)            */
+#define B200MEL_PAD_HIFI 1   /* reflect (n_fft-hop)/2 each side, then no centring
+                                (Audio2Mel models/transforms.py:352-360; interface/hifi_gan.py:48-54) */
+
+/* mel scale / normalisation of the filterbank */
+#define B200MEL_MEL_SLANEY 0 /* librosa.filters.mel default (htk=False)                     */
+#define B200MEL_MEL_HTK 1    /* torchaudio 0.7 MelScale (LogMelSpectrogramTorchAudio :383-385) */
+#define B200MEL_NORM_NONE 0
+#define B200MEL_NORM_SLANEY 1 /* librosa default: rows scaled by 2/(f[i+2]-f[i]) */
+
+/* log epilogue */
+#define B200MEL_LOG_NONE 0        /* linear mel                                               */
+#define B200MEL_LOG_LN_OFFSET 1   /* ln(mel + arg)        LogMelSpectrogram.forward :238      */
+#define B200MEL_LOG_LN_FLOOR 2    /* ln(max(mel, arg))    interface/hifi_gan.py:61            */
+#define B200MEL_LOG_LOG10_FLOOR 3 /* log10(max(mel, arg)) Audio2Mel.forward :365              */
+
+/* optional spectrum outputs (B, n_fft/2+1, T) */
+#define B200MEL_SPEC_NONE 0
+#define B200MEL_SPEC_MAG_PHASE 1 /* out_a = |X|, out_b = atan2(im, re)   STFT.transform :69, STFTTorchAudio.transform :311 */
+#define B200MEL_SPEC_RE_IM 2     /* out_a = re,  out_b = im              STFTTorchAudio.forward :297-303                  */
+#define B200MEL_SPEC_MAG 3       /* out_a = |X| only                                                                     */
+
+/* Geometry of one extractor.  Mirrors the constructor arguments of
+ * LogMelSpectrogram (models/transforms.py:211-213), Audio2Mel (:327-336),
+ * interface.hifi_gan.MelSpectrogram (interface/hifi_gan.py:34-35) and the
+ * constants of settings.py:9-22. */
+typedef struct b200mel_config {
+    int32_t struct_size; /* = sizeof(b200mel_config), for forward compatibility */
+    int32_t sample_rate;
+    int32_t n_fft;      /* supported: 1024, 2048 */
+    int32_t win_length; /* <= n_fft; periodic Hann, centre-padded to n_fft (models/transforms.py:30-31) */
+    int32_t hop_length;
+    int32_t n_mels; /* 0 = spectrum-only plan (STFT / STFTTorchAudio) */
+    float fmin;
+    float fmax; /* <= 0 means sample_rate / 2 (librosa default) */
+    int32_t pad_mode;  /* B200MEL_PAD_*  */
+    int32_t mel_scale; /* B200MEL_MEL_*  */
+    int32_t mel_norm;  /* B200MEL_NORM_* */
+    int32_t power;     /* 1 = magnitude (all pytorch_sound modules), 2 = power (torchaudio variant) */
+    float mag_eps;     /* added under the sqrt: 0 or 1e-9 (interface/hifi_gan.py:55) */
+} b200mel_config;
+
+/* Per-call epilogue.  log_arg is a forward() argument in the reference
+ * (LogMelSpectrogram.forward(wav, log_offset=1e-6)), so it is per call here. */
+typedef struct b200mel_epilogue {
+    int32_t struct_size;
+    int32_t log_kind; /* B200MEL_LOG_* */
+    float log_arg;    /* offset or floor */
+    int32_t has_clamp_lo;
+    float clamp_lo; /* natural-log units, db2log(min_db) utils/calculate.py:10-19 */
+    int32_t has_clamp_hi;
+    float clamp_hi;
+    int32_t norm_mel; /* 1: (clamp(y, lo, hi) - lo)/(hi - lo)*2 - 1   utils/calculate.py:32-43 (needs both clamps) */
+} b200mel_epilogue;
+
+typedef struct b200mel_plan b200mel_plan; /* opaque */
+
+int b200mel_version(void);
+const char *b200mel_last_error(void);
+
+/* Host helpers (no GPU needed).  They restate the third-party arithmetic the
+ * reference calls so that the Python shim can keep `mel_filter` / `window`
+ * buffers with the reference's names and values.
+ *   b200mel_mel_filterbank  <- librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax) (librosa 0.8.0;
+ *                              call sites models/transforms.py:220,339-341, interface/hifi_gan.py:42)
+ *   b200mel_hann_window     <- scipy.signal.get_window('hann', win, fftbins=True) + librosa.util.pad_center
+ *                              (models/transforms.py:30-31) == torch.hann_window(win) (:287) */
+int b200mel_mel_filterbank(int32_t sample_rate, int32_t n_fft, int32_t n_mels, double fmin, double fmax,
+                           int32_t mel_scale, int32_t mel_norm, float *out /* [n_mels][n_fft/2+1] */);
+int b200mel_hann_window(int32_t win_length, int32_t n_fft, float *out /* [n_fft] */);
+
+/* Number of frames for clips of L samples:
+ * centre: 1 + L/hop; hifi: (L + 2*((n_fft-hop)/2) - n_fft)/hop + 1.  */
+int b200mel_out_frames(const b200mel_plan *plan, int64_t L, int64_t *T);
+
+/* Create a plan on the CURRENT CUDA device (cudaGetDevice).  Builds window,
+ * twiddle tables and the banded (CSR-like) filterbank and uploads them. */
+int b200mel_plan_create(const b200mel_config *cfg, b200mel_plan **out);
+/* Replace the plan's filterbank by caller-provided weights (HOST pointer,
+ * row-major [n_mels][n_fft/2+1]) — used when a state_dict supplied a
+ * different `mel_filter`.  Not thread-safe against concurrent forward calls. */
+int b200mel_plan_set_filterbank(b200mel_plan *plan, const float *weights, int32_t n_mels, int32_t n_freq);
+int b200mel_plan_destroy(b200mel_plan *plan);
+
+/* One launch of the fused kernel over a clip batch.
+ *   wav        device pointer, float32, B rows of L valid samples, row r at wav + r*row_stride
+ *   lengths    nullable device pointer int32[B]: valid samples per clip (<= L).  Reflection happens
+ *              at the clip's own end and frames t >= frames(lengths[b]) are written as 0
+ *              (SpeechDataLoader.pad_collate_fn semantics, data/dataset.py:196-250).
+ *   out_mel    nullable device pointer float32 (B, n_mels, T) contiguous, T from b200mel_out_frames(L)
+ *   out_a/out_b nullable, (B, n_fft/2+1, T), meaning given by spec_kind
+ *   stream     CUDA stream handle (cudaStream_t) or NULL
+ * Replaces: LogMelSpectrogram.forward (models/transforms.py:231-244), STFT.transform (:53-69),
+ * STFTTorchAudio.forward/transform (:297-311), Audio2Mel.forward (:351-366),
+ * interface.hifi_gan.MelSpectrogram.forward (interface/hifi_gan.py:46-63). */
+int b200mel_forward(const b200mel_plan *plan, const float *wav, int64_t B, int64_t L, int64_t row_stride,
+                    const int32_t *lengths, const b200mel_epilogue *epi, float *out_mel, int32_t spec_kind,
+                    float *out_a, float *out_b, void *stream);
+
+/* Same, but wav_host / out_mel_host are HOST pointers (pinned memory gives
+ * asynchronous copies): H2D copy -> kernel -> D2H copy on `stream` using
+ * plan-owned device staging that grows on demand (so this entry point is NOT
+ * re-entrant on one plan).  It returns after enqueuing; the caller synchronises
+ * the stream.  This is the "host buffers in, host buffers out" call the
+ * reference's CPU modules correspond to (wav on CPU in, mel on CPU out). */
+int b200mel_forward_host(b200mel_plan *plan, const float *wav_host, int64_t B, int64_t L, int64_t row_stride,
+                         const b200mel_epilogue *epi, float *out_mel_host, void *stream);
+
+/* Number of kernel launches issued through this library since load (all plans;
+ * used by bench.py's gpu_launches claim). */
+int64_t b200mel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MEL_H */

@@ -1,0 +1,62 @@
+"""Post-collate GPU feature hook for the SpeechDataset / SpeechDataLoader path.
+
+In the reference, spectral features are either computed per item on the CPU inside DataLoader
+workers (`extra_features=[(column, callable)]`, data/dataset.py:24,41-45,85-90) or by the user's
+`Trainer.forward` on the collated CUDA batch (trainer.py:202).  `GpuFeatureLoader` wraps any
+SpeechDataLoader-like iterable in the MAIN process: every batch (a list of tensors produced by
+`pad_collate_fn`, data/dataset.py:196-228) is moved to the device the way `to_device` does
+(utils/tensor.py:6-15) and the requested feature tensors are appended where `extra_features`
+columns would sit — after the data columns and before the trailing mask (data/dataset.py:85-93).
+"""
+from typing import Callable, Iterable, List, Optional, Sequence, Tuple
+
+import torch
+
+
+class GpuFeatureLoader:
+    """features: [(batch_index, module)] — module(wav (B, L)) -> (B, C, T) on the GPU.
+
+    `mask_index` (optional): index of the wav-level mask of ones that SpeechDataset appends when
+    `is_mask=True` (data/dataset.py:73-74,92-93).  When given, per-clip lengths are derived from it and
+    passed to modules that accept `lengths=` so padded tails behave as per-item `extra_features` +
+    zero padding would (reflect at the clip's own end, zero frames beyond it)."""
+
+    def __init__(self, loader: Iterable, features: Sequence[Tuple[int, Callable]], device: Optional[str] = None,
+                 mask_index: Optional[int] = None):
+        self.loader = loader
+        self.features = list(features)
+        self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        self.mask_index = mask_index
+        for _, mod in self.features:
+            if isinstance(mod, torch.nn.Module):
+                mod.to(self.device)
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _to_device(self, batch) -> List[torch.Tensor]:
+        return [x.to(self.device, non_blocking=True) if isinstance(x, torch.Tensor) else x for x in batch]
+
+    def attach(self, batch) -> List[torch.Tensor]:
+        batch = self._to_device(batch)
+        lengths = None
+        if self.mask_index is not None:
+            lengths = batch[self.mask_index].to(torch.float32).sum(dim=-1).to(torch.int32)
+        feats = []
+        for idx, mod in self.features:
+            wav = batch[idx]
+            if lengths is not None:
+                try:
+                    feats.append(mod(wav, lengths=lengths))
+                    continue
+                except TypeError:
+                    pass
+            feats.append(mod(wav))
+        if self.mask_index is not None:
+            m = self.mask_index % len(batch)
+            return batch[:m] + feats + batch[m:]
+        return batch + feats
+
+    def __iter__(self):
+        for batch in self.loader:
+            yield self.attach(batch)

@@ -1,0 +1,230 @@
+"""Spectral operators with the names, constructor arguments, buffers and outputs of
+pytorch_sound/models/transforms.py — computed by the fused sm_100a kernel (libb200mel.so).
+
+    reference symbol (file:line)                         here
+    STFT.transform            transforms.py:53-69        STFT.transform           -> (mag, phase)
+    LogMelSpectrogram.forward transforms.py:231-244      LogMelSpectrogram.forward(wav, log_offset=1e-6)
+    STFTTorchAudio.forward    transforms.py:297-303      STFTTorchAudio.forward   -> (real, imag)
+    STFTTorchAudio.transform  transforms.py:305-311      STFTTorchAudio.transform -> (mag, phase)
+    Audio2Mel.forward         transforms.py:351-366      Audio2Mel.forward(audio (B,1,L))
+    MelToMFCC.forward         transforms.py:428-430      MelToMFCC.forward (small DCT matmul on the result)
+
+Inputs must be CUDA float32; there is no CPU path.  The modules are forward-only (feature
+extraction); the reference's trainable / synthesis-direction classes (LearnableSTFT, PQMF,
+STFT.inverse's use in vocoding) are outside the hot path and are not provided here.
+"""
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib, functional
+
+
+def _db_to_log(db: Optional[float]) -> Optional[float]:
+    # `if min_db:` truthiness as in the reference (transforms.py:222-229): 0 / None mean "no clamp"
+    if db:
+        return float(np.log(np.power(10.0, db / 10.0)))
+    return None
+
+
+class _PlanUser(nn.Module):
+    """Shared plumbing: plan lookup per device, custom-filterbank handling after load_state_dict."""
+
+    _fb_buffer_name: Optional[str] = None
+
+    def __init__(self):
+        super().__init__()
+        self._plan_kwargs = {}
+        self._private_plans = {}
+        self._fb_dirty = False
+        self._fb_default: Optional[torch.Tensor] = None
+
+    def _plan(self, device: torch.device) -> "_lib.Plan":
+        if device.type != 'cuda':
+            raise RuntimeError(functional.NO_CPU_MSG)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if not self._fb_dirty:
+            return _lib.cached_plan(idx, **self._plan_kwargs)
+        # a state_dict replaced the filterbank: use a private plan carrying those weights
+        pl = self._private_plans.get(idx)
+        if pl is None:
+            pl = _lib.Plan(_lib.make_config(**self._plan_kwargs), idx)
+            pl.set_filterbank(getattr(self, self._fb_buffer_name).detach().cpu().numpy())
+            self._private_plans[idx] = pl
+        return pl
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        name = self._fb_buffer_name
+        if name is not None and prefix + name in state_dict and self._fb_default is not None:
+            loaded = getattr(self, name).detach().cpu()
+            if loaded.shape != self._fb_default.shape or not torch.equal(loaded, self._fb_default):
+                self._fb_dirty = True
+                self._private_plans = {}
+
+
+class STFT(_PlanUser):
+    """Drop-in for pytorch_sound.models.transforms.STFT (transforms.py:13-101), analysis direction.
+
+    Same constructor; `transform(wav (B, L)) -> (magnitude, phase)`, each (B, filter_length//2+1,
+    1 + L//hop).  Registers `square_window`, like the reference; the 4 MB `forward_basis` /
+    `inverse_basis` conv kernels of the reference are not materialised (no conv is run) and are
+    ignored if present in a loaded state_dict.
+    """
+
+    def __init__(self, filter_length: int = 1024, hop_length: int = 512, win_length: int = None,
+                 window: str = 'hann'):
+        super().__init__()
+        self.filter_length = filter_length
+        self.hop_length = hop_length
+        self.win_length = win_length if win_length else filter_length
+        self.window = window
+        self.pad_amount = self.filter_length // 2
+        assert (filter_length >= self.win_length)
+        if window != 'hann':
+            raise NotImplementedError(f'{window} is not implemented ! Use hann')
+        fft_window = torch.from_numpy(_lib.hann_window(self.win_length, filter_length))
+        self.register_buffer('square_window', fft_window ** 2)
+        self._plan_kwargs = dict(sample_rate=1, n_fft=filter_length, win_length=self.win_length,
+                                 hop_length=hop_length, n_mels=0, pad_mode=_lib.PAD_CENTER)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        for k in ('forward_basis', 'inverse_basis'):
+            state_dict.pop(prefix + k, None)
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def transform(self, wav: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        _, mag, phase = functional.run(self._plan(wav.device), wav, None, want_mel=False,
+                                       spec_kind=_lib.SPEC_MAG_PHASE)
+        return mag, phase
+
+    def magnitude(self, wav: torch.Tensor) -> torch.Tensor:
+        """transform() without the phase pass (half the HBM writes)."""
+        _, mag, _ = functional.run(self._plan(wav.device), wav, None, want_mel=False, spec_kind=_lib.SPEC_MAG)
+        return mag
+
+    def forward(self, wav: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self.transform(wav)
+
+
+class LogMelSpectrogram(_PlanUser):
+    """Drop-in for pytorch_sound.models.transforms.LogMelSpectrogram (transforms.py:206-244).
+
+    forward(wav (B, L), log_offset=1e-6) -> (B, mel_size, 1 + L//hop) = clamp(ln(mel_filter @ |STFT| + log_offset)).
+    As in the reference the STFT uses filter_length = win_length (transforms.py:217), so n_fft must
+    equal win_length (otherwise the reference's own matmul shapes mismatch).
+    """
+
+    _fb_buffer_name = 'mel_filter'
+
+    def __init__(self, sample_rate: int, mel_size: int, n_fft: int, win_length: int,
+                 hop_length: int, min_db: float = None, max_db: float = None,
+                 mel_min: float = 0., mel_max: float = None):
+        super().__init__()
+        if n_fft != win_length:
+            raise ValueError("LogMelSpectrogram needs n_fft == win_length: the reference builds "
+                             "STFT(filter_length=win_length) and a (mel_size, n_fft//2+1) filter (transforms.py:217-221)")
+        self.mel_size = mel_size
+        self.stft = STFT(filter_length=win_length, hop_length=hop_length)
+        mel_filter = _lib.mel_filterbank(sample_rate, n_fft, mel_size, mel_min, mel_max)
+        self.register_buffer('mel_filter', torch.from_numpy(mel_filter))
+        self._fb_default = torch.from_numpy(mel_filter).clone()
+        self.min_db = _db_to_log(min_db)
+        self.max_db = _db_to_log(max_db)
+        self._plan_kwargs = dict(sample_rate=sample_rate, n_fft=n_fft, win_length=win_length, hop_length=hop_length,
+                                 n_mels=mel_size, fmin=mel_min, fmax=mel_max, pad_mode=_lib.PAD_CENTER)
+
+    def forward(self, wav: torch.Tensor, log_offset: float = 1e-6, lengths: Optional[torch.Tensor] = None,
+                norm: bool = False) -> torch.Tensor:
+        """`lengths` (int32 (B,), optional, extension): true clip lengths of a zero-padded batch — reflect at
+        each clip's own end and zero the frames past it.  `norm=True` (extension) fuses utils.calculate.norm_mel."""
+        epi = _lib.make_epilogue(_lib.LOG_LN_OFFSET, log_offset, self.min_db, self.max_db, norm)
+        mel, _, _ = functional.run(self._plan(wav.device), wav, epi, lengths=lengths)
+        return mel
+
+
+class STFTTorchAudio(_PlanUser):
+    """Drop-in for pytorch_sound.models.transforms.STFTTorchAudio (transforms.py:271-319), analysis direction."""
+
+    def __init__(self, filter_length: int = 1024, hop_length: int = 512, win_length: int = None, n_fft: int = None,
+                 window: str = 'hann'):
+        super().__init__()
+        self.filter_length = filter_length
+        self.hop_length = hop_length
+        self.win_length = win_length if win_length else self.filter_length
+        if window == 'hann':
+            self.register_buffer('window', torch.from_numpy(_lib.hann_window(self.win_length)))
+        else:
+            raise NotImplementedError(f'{window} is not implemented ! Use hann')
+        self.n_fft = n_fft if n_fft else self.win_length
+        self._plan_kwargs = dict(sample_rate=1, n_fft=self.n_fft, win_length=self.win_length, hop_length=hop_length,
+                                 n_mels=0, pad_mode=_lib.PAD_CENTER)
+
+    def forward(self, wav: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        _, re, im = functional.run(self._plan(wav.device), wav, None, want_mel=False, spec_kind=_lib.SPEC_RE_IM)
+        return re, im
+
+    def transform(self, wav: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        _, mag, phase = functional.run(self._plan(wav.device), wav, None, want_mel=False,
+                                       spec_kind=_lib.SPEC_MAG_PHASE)
+        return mag, phase
+
+
+class Audio2Mel(_PlanUser):
+    """Drop-in for pytorch_sound.models.transforms.Audio2Mel (MelGAN front-end, transforms.py:322-366).
+
+    forward(audio (B, 1, L)) -> (B, n_mel_channels, L // hop) = log10(max(mel_basis @ |STFT|, 1e-5)).
+    """
+
+    _fb_buffer_name = 'mel_basis'
+
+    def __init__(self, n_fft: int = 1024, hop_length: int = 256, win_length: int = 1024, sampling_rate: int = 22050,
+                 n_mel_channels: int = 80, mel_fmin: float = 0.0, mel_fmax: float = None):
+        super().__init__()
+        mel_basis = _lib.mel_filterbank(sampling_rate, n_fft, n_mel_channels, mel_fmin, mel_fmax)
+        self.register_buffer("mel_basis", torch.from_numpy(mel_basis))
+        self._fb_default = torch.from_numpy(mel_basis).clone()
+        self.register_buffer("window", torch.from_numpy(_lib.hann_window(win_length)))
+        self.n_fft = n_fft
+        self.hop_length = hop_length
+        self.win_length = win_length
+        self.sampling_rate = sampling_rate
+        self.n_mel_channels = n_mel_channels
+        self._plan_kwargs = dict(sample_rate=sampling_rate, n_fft=n_fft, win_length=win_length,
+                                 hop_length=hop_length, n_mels=n_mel_channels, fmin=mel_fmin, fmax=mel_fmax,
+                                 pad_mode=_lib.PAD_HIFI)
+        self._epi = _lib.make_epilogue(_lib.LOG_LOG10_FLOOR, 1e-5)
+
+    def forward(self, audio: torch.Tensor) -> torch.Tensor:
+        if audio.dim() == 3:
+            if audio.shape[1] != 1:
+                raise ValueError("Audio2Mel expects (B, 1, L)")
+            audio = audio[:, 0]
+        mel, _, _ = functional.run(self._plan(audio.device), audio, self._epi)
+        return mel
+
+
+class MelToMFCC(nn.Module):
+    """pytorch_sound.models.transforms.MelToMFCC (transforms.py:419-430): ortho DCT-II of a mel spectrogram.
+    The (n_mfcc x mel_size) matmul is a tiny post-op on the kernel's output; torchaudio's
+    functional.create_dct is restated so torchaudio is not needed."""
+
+    def __init__(self, n_mfcc: int, mel_size: int, norm: str = 'ortho'):
+        super().__init__()
+        self.n_mfcc = n_mfcc
+        n = torch.arange(float(mel_size))
+        k = torch.arange(float(n_mfcc)).unsqueeze(1)
+        dct = torch.cos(np.pi / float(mel_size) * (n + 0.5) * k)  # (n_mfcc, mel_size)
+        if norm is None:
+            dct *= 2.0
+        else:
+            assert norm == 'ortho'
+            dct[0] *= 1.0 / np.sqrt(2.0)
+            dct *= np.sqrt(2.0 / float(mel_size))
+        self.register_buffer('dct_mat', dct)
+
+    def forward(self, mel_spec: torch.Tensor) -> torch.Tensor:
+        assert len(mel_spec.size()) == 3
+        return torch.matmul(self.dct_mat, mel_spec)

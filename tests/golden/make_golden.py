@@ -1,0 +1,165 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference modules.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+It imports /root/reference/pytorch_sound/models/transforms.py,
+interface/hifi_gan.py and utils/calculate.py as they are and records their
+outputs on seeded inputs.  To make the 2020-era reference importable on this
+image (torch 2.11, no librosa) three third-party names are shimmed BEFORE import:
+
+  * `librosa` is absent: a stub module provides `librosa.filters.mel` (the oracle's
+    restatement of librosa 0.8.0 — so the filterbank itself is NOT pinned by this
+    script, only everything around it) and `librosa.util.pad_center`;
+  * `scipy.signal.kaiser` moved to scipy.signal.windows (only imported by the
+    reference's PQMF, unused here);
+  * `torch.stft` lost its legacy real-valued return: a wrapper restores the
+    torch 1.7 behaviour `view_as_real(stft(..., return_complex=True))`;
+  * `unidecode` / `inflect` (text cleaners pulled in by settings.py) are stubbed.
+
+Nothing under /root/reference is modified or copied.  The GPU box never runs this.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+
+def install_shims():
+    import scipy.signal
+    import scipy.signal.windows
+    import torch
+
+    from oracle import mel_oracle
+
+    if not hasattr(scipy.signal, "kaiser"):
+        scipy.signal.kaiser = scipy.signal.windows.kaiser
+
+    librosa = types.ModuleType("librosa")
+    filters = types.ModuleType("librosa.filters")
+    util = types.ModuleType("librosa.util")
+
+    def mel(sr, n_fft, n_mels=128, fmin=0.0, fmax=None, htk=False, norm="slaney"):
+        return mel_oracle.mel_filterbank(sr, n_fft, n_mels, fmin, fmax, htk, norm)
+
+    def pad_center(data, size, axis=-1):
+        n = data.shape[axis]
+        lpad = int((size - n) // 2)
+        lengths = [(0, 0)] * data.ndim
+        lengths[axis] = (lpad, int(size - n - lpad))
+        return np.pad(data, lengths)
+
+    filters.mel = mel
+    util.pad_center = pad_center
+    librosa.filters = filters
+    librosa.util = util
+    sys.modules["librosa"] = librosa
+    sys.modules["librosa.filters"] = filters
+    sys.modules["librosa.util"] = util
+    for name in ("unidecode", "inflect"):
+        m = types.ModuleType(name)
+        m.unidecode = lambda s: s
+        m.engine = lambda: None
+        sys.modules[name] = m
+
+    real_stft = torch.stft
+
+    def legacy_stft(input, n_fft, hop_length=None, win_length=None, window=None, center=True, pad_mode="reflect",
+                    normalized=False, onesided=None, return_complex=None):
+        if return_complex is None:
+            out = real_stft(input, n_fft, hop_length, win_length, window, center, pad_mode, normalized, onesided,
+                            return_complex=True)
+            return torch.view_as_real(out)
+        return real_stft(input, n_fft, hop_length, win_length, window, center, pad_mode, normalized, onesided,
+                         return_complex=return_complex)
+
+    torch.stft = legacy_stft
+
+
+def main():
+    import torch
+
+    install_shims()
+    sys.path.insert(0, REF)
+    from pytorch_sound.models import transforms as T
+    from pytorch_sound.interface.hifi_gan import MelSpectrogram
+    from pytorch_sound.utils import calculate
+    from pytorch_sound import settings
+
+    from oracle import mel_oracle
+
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+    out = {}
+
+    # C1 of BASELINE.json: 1 x 22050 pure sine at the settings.py geometry
+    n = np.arange(22050)
+    c1 = (0.5 * np.sin(2 * np.pi * 440.0 * n / 22050)).astype(np.float32)[None]
+    # seeded sine+noise clips with a length that is not a multiple of hop
+    clips = mel_oracle.synth_clips(4, 6000, 22050, seed=20261017)
+    noise = np.random.default_rng(7).uniform(-1, 1, size=(3, 4099)).astype(np.float32)
+
+    geo = dict(sample_rate=settings.SAMPLE_RATE, mel_size=settings.MEL_SIZE, n_fft=settings.N_FFT,
+               win_length=settings.WIN_LENGTH, hop_length=settings.HOP_LENGTH, mel_min=float(settings.MEL_MIN),
+               mel_max=float(settings.MEL_MAX))
+    out["settings"] = np.array([settings.SAMPLE_RATE, settings.N_FFT, settings.WIN_LENGTH, settings.HOP_LENGTH,
+                                settings.SPEC_SIZE, settings.MEL_SIZE, settings.MEL_MIN, settings.MEL_MAX,
+                                settings.MIN_DB, settings.MAX_DB], dtype=np.int64)
+
+    for name, x in (("c1", c1), ("clips", clips), ("noise", noise)):
+        xt = torch.from_numpy(x)
+        out[f"{name}.wav"] = x
+        with torch.no_grad():
+            lm = T.LogMelSpectrogram(min_db=settings.MIN_DB, max_db=settings.MAX_DB, **geo)
+            out[f"{name}.logmel_clamped"] = lm(xt).numpy()
+            lm_nc = T.LogMelSpectrogram(**geo)
+            out[f"{name}.logmel"] = lm_nc(xt).numpy()
+            out[f"{name}.logmel_off1e-3"] = lm_nc(xt, log_offset=1e-3).numpy()
+            st = T.STFT(filter_length=1024, hop_length=256)
+            mag, phase = st.transform(xt)
+            out[f"{name}.stft_mag"] = mag.numpy()
+            out[f"{name}.stft_phase"] = phase.numpy()
+            sta = T.STFTTorchAudio(filter_length=1024, hop_length=256)
+            re, im = sta(xt)
+            out[f"{name}.stfta_re"] = re.numpy()
+            out[f"{name}.stfta_im"] = im.numpy()
+            mag2, phase2 = sta.transform(xt)
+            out[f"{name}.stfta_mag"] = mag2.numpy()
+            a2m = T.Audio2Mel()
+            out[f"{name}.audio2mel"] = a2m(xt.unsqueeze(1)).numpy()
+            hf = MelSpectrogram()
+            out[f"{name}.hifi"] = hf(xt).numpy()
+            out[f"{name}.norm_mel"] = calculate.norm_mel(lm(xt)).numpy()
+
+    # n_fft = 2048 geometry (BASELINE config C4: 44100 Hz, hop 512, 128 mels)
+    x4 = mel_oracle.synth_clips(2, 9000, 44100, seed=20261017 + 4000)
+    out["c4.wav"] = x4
+    with torch.no_grad():
+        lm4 = T.LogMelSpectrogram(sample_rate=44100, mel_size=128, n_fft=2048, win_length=2048, hop_length=512)
+        out["c4.logmel"] = lm4(torch.from_numpy(x4)).numpy()
+        a2m4 = T.Audio2Mel(n_fft=2048, hop_length=512, win_length=2048, sampling_rate=44100, n_mel_channels=128)
+        out["c4.audio2mel"] = a2m4(torch.from_numpy(x4).unsqueeze(1)).numpy()
+
+    # buffers the reference modules register (state_dict compatibility targets)
+    out["buf.mel_filter"] = lm.mel_filter.numpy()
+    out["buf.hifi_window"] = hf.window.numpy()
+    out["buf.stft_window_sq"] = st.square_window.numpy()
+    out["kat.db2log"] = np.array([calculate.db2log(np.array(float(settings.MIN_DB))),
+                                  calculate.db2log(np.array(float(settings.MAX_DB)))])
+    xs = torch.linspace(-1, 1, 11)
+    out["kat.unnorm_mel"] = calculate.unnorm_mel(xs).numpy()
+
+    path = os.path.join(HERE, "reference_outputs.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

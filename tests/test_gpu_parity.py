@@ -1,0 +1,308 @@
+"""Parity of the CUDA path (through the C ABI, via the reference-shaped modules) against the float64
+oracle, the committed reference outputs, and size-independent properties.  Needs a B200: `-m gpu`."""
+import numpy as np
+import pytest
+
+from oracle import mel_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # |y - y_ref64| <= 1e-4 * max(1, |y_ref64|), north-star / SURVEY 8d
+
+
+@pytest.fixture(scope="module")
+def torch_cuda(built_lib):
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need CUDA"
+    return torch
+
+
+def cuda(torch, x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+GEO = dict(sample_rate=22050, mel_size=80, n_fft=1024, win_length=1024, hop_length=256, mel_min=0.0, mel_max=8000.0)
+
+
+# ------------------------------------------------------------------ against the reference's own outputs
+@pytest.mark.parametrize("name", ["c1", "clips", "noise"])
+def test_golden_reference_outputs(torch_cuda, golden, name):
+    torch = torch_cuda
+    from pytorch_sound_b200.interface.hifi_gan import MelSpectrogram
+    from pytorch_sound_b200.models import transforms as T
+    from pytorch_sound_b200.utils.calculate import norm_mel
+
+    wav = cuda(torch, golden[f"{name}.wav"])
+    tol = 5e-3 if name == "c1" else TOL  # C1 = pure sine on the fp32 noise floor of the REFERENCE
+    lm = T.LogMelSpectrogram(min_db=-50, max_db=30, **GEO).cuda()
+    y = lm(wav)
+    assert y.shape == golden[f"{name}.logmel_clamped"].shape and y.dtype == torch.float32
+    assert mo.parity_error(y.cpu().numpy(), golden[f"{name}.logmel_clamped"]) < tol
+    y2 = T.LogMelSpectrogram(**GEO).cuda()(wav, log_offset=1e-3)
+    assert mo.parity_error(y2.cpu().numpy(), golden[f"{name}.logmel_off1e-3"]) < TOL
+    np.testing.assert_allclose(norm_mel(y).cpu().numpy(), golden[f"{name}.norm_mel"], atol=2e-3 if name == "c1" else 2e-4)
+    np.testing.assert_allclose(lm(wav, norm=True).cpu().numpy(), golden[f"{name}.norm_mel"],
+                               atol=2e-3 if name == "c1" else 2e-4)
+
+    mag, phase = T.STFT(filter_length=1024, hop_length=256).cuda().transform(wav)
+    scale = float(golden[f"{name}.stft_mag"].max())
+    assert np.abs(mag.cpu().numpy() - golden[f"{name}.stft_mag"]).max() < 3e-6 * scale
+    strong = golden[f"{name}.stft_mag"] > 1e-2 * scale
+    d = np.angle(np.exp(1j * (phase.cpu().numpy().astype(np.float64) - golden[f"{name}.stft_phase"])))
+    assert np.abs(d[strong]).max() < 1e-3
+    sta = T.STFTTorchAudio(filter_length=1024, hop_length=256).cuda()
+    re, im = sta(wav)
+    assert np.abs(re.cpu().numpy() - golden[f"{name}.stfta_re"]).max() < 2e-6 * scale
+    assert np.abs(im.cpu().numpy() - golden[f"{name}.stfta_im"]).max() < 2e-6 * scale
+    mag2, _ = sta.transform(wav)
+    assert np.abs(mag2.cpu().numpy() - golden[f"{name}.stfta_mag"]).max() < 2e-6 * scale
+
+    a2m = T.Audio2Mel().cuda()(wav.unsqueeze(1))
+    assert a2m.shape == golden[f"{name}.audio2mel"].shape
+    assert mo.parity_error(a2m.cpu().numpy(), golden[f"{name}.audio2mel"]) < (2e-3 if name == "c1" else TOL)
+    hf = MelSpectrogram().cuda()(wav)
+    assert hf.shape == golden[f"{name}.hifi"].shape
+    assert mo.parity_error(hf.cpu().numpy(), golden[f"{name}.hifi"]) < (2e-3 if name == "c1" else TOL)
+
+
+def test_golden_n_fft_2048(torch_cuda, golden):
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+
+    wav = cuda(torch, golden["c4.wav"])
+    y = T.LogMelSpectrogram(sample_rate=44100, mel_size=128, n_fft=2048, win_length=2048, hop_length=512).cuda()(wav)
+    assert y.shape == (2, 128, 18)
+    assert mo.parity_error(y.cpu().numpy(), golden["c4.logmel"]) < TOL
+    a = T.Audio2Mel(n_fft=2048, hop_length=512, win_length=2048, sampling_rate=44100, n_mel_channels=128).cuda()(
+        wav.unsqueeze(1))
+    assert mo.parity_error(a.cpu().numpy(), golden["c4.audio2mel"]) < TOL
+
+
+# ------------------------------------------------------------------ against the float64 oracle, seeded inputs
+@pytest.mark.parametrize("B,L", [(1, 22050), (64, 22050), (3, 1025), (5, 8000), (2, 513), (7, 5000), (2, 70001)])
+def test_logmel_vs_oracle(torch_cuda, B, L):
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+
+    x = mo.synth_clips(B, L, 22050, seed=20261017 + 2000)
+    y = T.LogMelSpectrogram(**GEO).cuda()(cuda(torch, x)).cpu().numpy()  # pre-clamp log-mel
+    ref = mo.log_mel_spectrogram(x, **GEO, clamp=False)
+    assert y.shape == ref.shape == (B, 80, 1 + L // 256)
+    assert mo.parity_error(y, ref) < TOL
+
+
+@pytest.mark.parametrize("hop,win", [(256, 1024), (512, 1024), (100, 1024), (1024, 1024), (300, 800), (1, 1024)])
+def test_stft_geometries_vs_oracle(torch_cuda, hop, win):
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+
+    L = 3000 if hop > 1 else 1100
+    x = mo.synth_clips(3, L, 22050, seed=5)
+    st = T.STFT(filter_length=1024, hop_length=hop, win_length=win).cuda()
+    mag, phase = st.transform(cuda(torch, x))
+    rm, rp = mo.stft_transform(x, 1024, hop, win)
+    assert mag.shape == rm.shape
+    assert np.abs(mag.cpu().numpy() - rm).max() < 2e-6 * rm.max()
+    assert np.abs(st.magnitude(cuda(torch, x)).cpu().numpy() - rm).max() < 2e-6 * rm.max()
+    strong = rm > 1e-2 * rm.max()
+    d = np.angle(np.exp(1j * (phase.cpu().numpy() - rp)))
+    assert np.abs(d[strong]).max() < 1e-4
+
+
+def test_c4_geometry_vs_oracle(torch_cuda):
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+
+    geo = dict(sample_rate=44100, mel_size=128, n_fft=2048, win_length=2048, hop_length=512)
+    x = mo.synth_clips(4, 44100, 44100, seed=20261017 + 4000)
+    y = T.LogMelSpectrogram(**geo).cuda()(cuda(torch, x)).cpu().numpy()
+    ref = mo.log_mel_spectrogram(x, **geo, clamp=False)
+    assert y.shape == ref.shape == (4, 128, 87)
+    assert mo.parity_error(y, ref) < TOL
+    sta = T.STFTTorchAudio(filter_length=2048, hop_length=512).cuda()
+    re, im = sta(cuda(torch, x))
+    s = mo.stft_complex(x, 2048, 512)
+    scale = np.abs(s).max()
+    assert np.abs(re.cpu().numpy() - s.real).max() < 2e-6 * scale
+    assert np.abs(im.cpu().numpy() - s.imag).max() < 2e-6 * scale
+
+
+def test_c5_geometry_vs_oracle(torch_cuda):
+    """VoiceBank-shaped: 0.5 s @ 16 kHz, fmax = Nyquist (the top mel band touches bin 512)."""
+    torch = torch_cuda
+    from pytorch_sound_b200.interface.hifi_gan import MelSpectrogram
+    from pytorch_sound_b200.models import transforms as T
+
+    geo = dict(sample_rate=16000, mel_size=80, n_fft=1024, win_length=1024, hop_length=256, mel_min=0.0, mel_max=8000.0)
+    x = mo.synth_clips(33, 8000, 16000, seed=20261017 + 5000)
+    y = T.LogMelSpectrogram(**geo).cuda()(cuda(torch, x)).cpu().numpy()
+    ref = mo.log_mel_spectrogram(x, **geo, clamp=False)
+    assert y.shape == (33, 80, 32)
+    assert mo.parity_error(y, ref) < TOL
+    h = MelSpectrogram(sampling_rate=16000).cuda()(cuda(torch, x)).cpu().numpy()
+    assert h.shape == (33, 80, 31)
+    assert mo.parity_error(h, mo.hifi_mel_spectrogram(x, sampling_rate=16000)) < TOL
+
+
+def test_hifi_and_audio2mel_vs_oracle(torch_cuda):
+    torch = torch_cuda
+    from pytorch_sound_b200.interface.hifi_gan import MelSpectrogram
+    from pytorch_sound_b200.models import transforms as T
+
+    x = mo.synth_clips(6, 22050, 22050, seed=11)
+    xg = cuda(torch, x)
+    h = MelSpectrogram().cuda()(xg).cpu().numpy()
+    assert h.shape == (6, 80, 86)
+    assert mo.parity_error(h, mo.hifi_mel_spectrogram(x)) < TOL
+    a = T.Audio2Mel().cuda()(xg.unsqueeze(1)).cpu().numpy()
+    assert mo.parity_error(a, mo.audio2mel(x)) < TOL
+    # is_center=True: explicit pad then torch.stft's own centring (interface/hifi_gan.py:48-54)
+    hc = MelSpectrogram().cuda()(xg, is_center=True).cpu().numpy()
+    xp = mo.reflect_pad(x.astype(np.float64), 384)
+    s = mo.stft_complex(xp, 1024, 256, 1024, pad=512)
+    fb = mo.mel_filterbank(22050, 1024, 80, 0.0, 8000.0).astype(np.float64)
+    ref = np.log(np.maximum(np.einsum("mf,bft->bmt", fb, np.sqrt(s.real ** 2 + s.imag ** 2 + 1e-9)), 1e-5))
+    assert hc.shape == ref.shape
+    assert mo.parity_error(hc, ref) < TOL
+
+
+# ------------------------------------------------------------------ edge cases
+def test_silence_and_floor(torch_cuda):
+    torch = torch_cuda
+    from pytorch_sound_b200.interface.hifi_gan import MelSpectrogram
+    from pytorch_sound_b200.models import transforms as T
+
+    z = torch.zeros(2, 4096, device="cuda")
+    y = T.LogMelSpectrogram(min_db=-50, max_db=30, **GEO).cuda()(z)
+    assert torch.all(y == y[0, 0, 0]) and abs(float(y[0, 0, 0]) - np.log(1e-5)) < 1e-6  # clamp_min(ln 1e-5)
+    y = T.LogMelSpectrogram(**GEO).cuda()(z)
+    assert abs(float(y.max()) - np.log(1e-6)) < 1e-5 and abs(float(y.min()) - np.log(1e-6)) < 1e-5
+    h = MelSpectrogram().cuda()(z)
+    ref = mo.hifi_mel_spectrogram(np.zeros((2, 4096)))  # sqrt(1e-9) magnitudes -> not at the floor everywhere
+    assert mo.parity_error(h.cpu().numpy(), ref) < TOL
+    loud = torch.full((1, 4096), 1000.0, device="cuda")
+    y = T.LogMelSpectrogram(min_db=-50, max_db=30, **GEO).cuda()(loud)
+    assert float(y.max()) <= np.log(1e3) + 1e-6
+
+
+def test_shortest_and_error_cases(torch_cuda):
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+
+    lm = T.LogMelSpectrogram(**GEO).cuda()
+    x = mo.synth_clips(2, 513, 22050, seed=3)  # shortest legal clip for reflect pad 512
+    assert mo.parity_error(lm(cuda(torch, x)).cpu().numpy(), mo.log_mel_spectrogram(x, **GEO, clamp=False)) < TOL
+    with pytest.raises(ValueError):
+        lm(torch.zeros(2, 512, device="cuda"))  # torch raises for reflect pad >= L too
+    with pytest.raises(RuntimeError):
+        lm(torch.zeros(2, 4096))  # CPU tensor: no fallback
+    with pytest.raises(TypeError):
+        lm(torch.zeros(2, 4096, device="cuda", dtype=torch.float64))
+    with pytest.raises(ValueError):
+        lm(torch.zeros(4096, device="cuda"))
+    with pytest.raises(ValueError):
+        T.STFT(filter_length=768, hop_length=256).cuda().transform(torch.zeros(1, 4096, device="cuda"))
+    assert lm(torch.zeros(0, 4096, device="cuda")).shape == (0, 80, 17)  # empty batch
+
+
+def test_non_contiguous_and_strided_rows(torch_cuda):
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+
+    lm = T.LogMelSpectrogram(**GEO).cuda()
+    x = mo.synth_clips(4, 6001, 22050, seed=9)
+    big = torch.zeros(4, 7000, device="cuda")
+    big[:, :6001] = cuda(torch, x)
+    view = big[:, :6001]  # row stride 7000 != L, unit column stride: consumed in place
+    ref = mo.log_mel_spectrogram(x, **GEO, clamp=False)
+    assert mo.parity_error(lm(view).cpu().numpy(), ref) < TOL
+    col = cuda(torch, np.ascontiguousarray(x.T)).t()  # column-major view -> one contiguous() copy in the shim
+    assert mo.parity_error(lm(col).cpu().numpy(), ref) < TOL
+
+
+def test_ragged_lengths(torch_cuda):
+    """Zero-padded variable-length batch (pad_collate_fn layout) with per-clip lengths: every clip must equal
+    the clip processed alone, frames past its end are zero."""
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+
+    lm = T.LogMelSpectrogram(**GEO).cuda()
+    lens = [9000, 513, 4097, 8999, 2560]
+    Lmax = max(lens)
+    batch = np.zeros((len(lens), Lmax), dtype=np.float32)
+    clips = [mo.synth_clips(1, n, 22050, seed=100 + i)[0] for i, n in enumerate(lens)]
+    for i, c in enumerate(clips):
+        batch[i, :len(c)] = c
+    y = lm(cuda(torch, batch), lengths=torch.tensor(lens, dtype=torch.int32, device="cuda")).cpu().numpy()
+    assert y.shape == (5, 80, 1 + Lmax // 256)
+    for i, c in enumerate(clips):
+        Ti = 1 + len(c) // 256
+        ref = mo.log_mel_spectrogram(c[None], **GEO, clamp=False)[0]
+        assert mo.parity_error(y[i, :, :Ti], ref) < TOL
+        assert np.all(y[i, :, Ti:] == 0.0)
+    # without lengths the padded batch is processed as-is (Trainer.forward semantics)
+    y2 = lm(cuda(torch, batch)).cpu().numpy()
+    assert mo.parity_error(y2, mo.log_mel_spectrogram(batch, **GEO, clamp=False)) < TOL
+
+
+def test_state_dict_filterbank_override(torch_cuda):
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+
+    lm = T.LogMelSpectrogram(**GEO).cuda()
+    sd = lm.state_dict()
+    assert set(sd) == {"mel_filter", "stft.square_window"}
+    rng = np.random.default_rng(0)
+    custom = np.abs(rng.standard_normal((80, 513))).astype(np.float32)
+    custom[:, 400:] = 0
+    sd2 = {k: v.clone() for k, v in sd.items()}
+    sd2["mel_filter"] = torch.from_numpy(custom)
+    sd2["stft.forward_basis"] = torch.zeros(1026, 1, 1024)  # reference checkpoints carry these
+    sd2["stft.inverse_basis"] = torch.zeros(1026, 1, 1024)
+    lm2 = T.LogMelSpectrogram(**GEO).cuda()
+    lm2.load_state_dict(sd2)
+    x = mo.synth_clips(2, 5000, 22050, seed=1)
+    mag, _ = mo.stft_transform(x, 1024, 256)
+    ref = np.log(np.einsum("mf,bft->bmt", custom.astype(np.float64), mag) + 1e-6)
+    assert mo.parity_error(lm2(cuda(torch, x)).cpu().numpy(), ref) < TOL
+    # the default module is unaffected (shared plan cache is not mutated)
+    assert mo.parity_error(lm(cuda(torch, x)).cpu().numpy(), mo.log_mel_spectrogram(x, **GEO, clamp=False)) < TOL
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE config C2)
+def test_c2_full_size_properties(torch_cuda):
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+
+    B, L = 256, 22050
+    x = mo.synth_clips(B, L, 22050, seed=20261017 + 2000)
+    xg = cuda(torch, x)
+    lm = T.LogMelSpectrogram(**GEO).cuda()
+    y = lm(xg)
+    assert y.shape == (B, 80, 87) and bool(torch.isfinite(y).all())
+    # (1) clip independence + determinism: any clip alone == that clip inside the batch, bit for bit
+    for i in (0, 1, 100, 255):
+        assert torch.equal(lm(xg[i:i + 1])[0], y[i])
+    assert torch.equal(lm(xg), y)
+    # (2) batch permutation equivariance
+    perm = torch.randperm(B, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
+    assert torch.equal(lm(xg[perm]), y[perm])
+    # (3) homogeneity of the magnitude path: |STFT(2x)| == 2|STFT(x)| exactly (power-of-two scaling)
+    st = T.STFT(filter_length=1024, hop_length=256).cuda()
+    m1 = st.magnitude(xg[:32])
+    m2 = st.magnitude(xg[:32] * 2)
+    assert torch.equal(m2, m1 * 2)
+    # (4) Parseval on interior frames: sum |X_k|^2 (two-sided) == N * sum (w x)^2
+    m = m1.double()
+    energy = m[:, 0] ** 2 + m[:, 512] ** 2 + 2 * (m[:, 1:512] ** 2).sum(1)
+    w = torch.from_numpy(mo.hann_periodic(1024).astype(np.float32)).double().cuda()
+    t = 10
+    seg = xg[:32, t * 256 - 512: t * 256 + 512].double() * w
+    assert torch.allclose(energy[:, t], 1024 * (seg ** 2).sum(1), rtol=1e-5)
+    # (5) oracle on the first 64 clips + all edge frames of every clip
+    ref = mo.log_mel_spectrogram(x[:64], **GEO, clamp=False)
+    assert mo.parity_error(y[:64].cpu().numpy(), ref) < TOL
+    edge = [0, 1, 2, 84, 85, 86]
+    ref_edges = mo.log_mel_spectrogram(x, **GEO, clamp=False)[:, :, edge]
+    assert mo.parity_error(y[:, :, edge].cpu().numpy(), ref_edges) < TOL
