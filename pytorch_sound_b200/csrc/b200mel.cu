@@ -5,21 +5,16 @@
 // (models/transforms.py:53-69, 231-244, 297-311, 351-366; interface/hifi_gan.py:46-63)
 // by ONE launch per clip batch.  See DESIGN.md for the data layout and roofline.
 //
-// Work decomposition (v1): one warp = one 1024-point complex FFT held entirely in
-// registers (32 complex values per lane, two radix-32 passes, one shared-memory
-// transpose):
-//   n_fft = 1024 ("pair" mode):  two consecutive real frames t, t+1 are packed as
-//        re/im of one complex FFT and separated with the conjugate-symmetry identity;
-//   n_fft = 2048 ("split" mode): one real frame is packed even/odd into a 1024-point
-//        complex FFT and finished with the real-input split pass.
-// The magnitudes go to a per-warp shared-memory tile, the banded (CSR) mel filterbank
-// is applied from there, the log/clamp epilogue runs in registers.
+// The kernel itself (persistent warps, TMA-staged samples, register-resident radix-32 FFT passes,
+// banded mel from shared memory, log epilogue in registers) lives in logmel_kernel.cuh; this file is the
+// host side: librosa/scipy restatements, plan construction, launch and the extern "C" surface.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <new>
 #include <string>
@@ -27,269 +22,9 @@
 
 #include "../../include/b200mel.h"
 #include "fft32.cuh"
+#include "logmel_kernel.cuh"
 
 namespace b200mel {
-
-// ----------------------------------------------------------------------------------------------
-// kernel parameters
-// ----------------------------------------------------------------------------------------------
-struct KParams {
-    const float *wav;
-    long long row_stride;
-    long long B;
-    int L;
-    const int *lengths;
-    int T, hop, pad, n_fft;
-    const float *window;    // [n_fft], periodic Hann centre-padded, pre-scaled by 0.5
-    const float2 *tw;       // [32][32]  tw[k1*32 + lane] = exp(-2 pi i k1 lane / 1024)
-    const float2 *tw_post;  // [32]      exp(-2 pi i lane / 2048)            (split mode)
-    int n_mels, n_freq;
-    const int *mel_lo;   // first bin of row m
-    const int *mel_cnt;  // number of bins of row m
-    const int *mel_ptr;  // offset of row m in mel_w
-    const float *mel_w;
-    float *out_mel, *out_a, *out_b;
-    int spec_kind;
-    float mag_eps;
-    int power;
-    int log_kind;
-    float log_arg;
-    int has_lo, has_hi, norm;
-    float lo, hi, norm_scale;
-    long long tasks_per_clip, n_tasks;
-};
-
-constexpr int kWarpsPerCta = 4;
-constexpr int kBufStride = 33;                   // float2 per transposed row (+1 pad)
-constexpr int kWarpBufElems = 32 * kBufStride;  // float2 per warp
-constexpr int kMagStride = 520;                  // floats between the two frames of a pair tile
-
-__device__ __forceinline__ int frames_of(int Li, int n_fft, int hop, int pad) {
-    int span = Li + 2 * pad - n_fft;
-    return span < 0 ? 0 : span / hop + 1;
-}
-
-__device__ __forceinline__ int reflect_index(int i, int Li) {
-    if (i < 0) i = -i;
-    if (i >= Li) i = 2 * (Li - 1) - i;
-    return min(max(i, 0), Li - 1);
-}
-
-__device__ __forceinline__ float epilogue(float x, const KParams &p) {
-    float y = x;
-    if (p.log_kind == B200MEL_LOG_LN_OFFSET)
-        y = logf(x + p.log_arg);
-    else if (p.log_kind == B200MEL_LOG_LN_FLOOR)
-        y = logf(fmaxf(x, p.log_arg));
-    else if (p.log_kind == B200MEL_LOG_LOG10_FLOOR)
-        y = log10f(fmaxf(x, p.log_arg));
-    if (p.has_lo) y = fmaxf(y, p.lo);
-    if (p.has_hi) y = fminf(y, p.hi);
-    if (p.norm) y = (y - p.lo) * p.norm_scale - 1.0f;
-    return y;
-}
-
-__device__ __forceinline__ float magnitude(float re, float im, const KParams &p) {
-    float sq = fmaf(re, re, im * im);
-    if (p.power == 2) return sq;
-    return sqrtf(sq + p.mag_eps);
-}
-
-// Store one spectrum bin (frame t of clip b) according to spec_kind.
-__device__ __forceinline__ void store_spec(const KParams &p, long long b, int k, int t, float re, float im,
-                                           float mag) {
-    long long o = (b * p.n_freq + k) * (long long)p.T + t;
-    if (p.spec_kind == B200MEL_SPEC_RE_IM) {
-        p.out_a[o] = re;
-        p.out_b[o] = im;
-    } else {
-        p.out_a[o] = mag;
-        if (p.spec_kind == B200MEL_SPEC_MAG_PHASE) p.out_b[o] = atan2f(im, re);
-    }
-}
-
-// kPair = true : n_fft 1024, the warp transforms frames (2q, 2q+1) of its clip
-// kPair = false: n_fft 2048, the warp transforms frame q of its clip
-template <bool kPair>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) logmel_warp_kernel(const KParams p) {
-    extern __shared__ float2 smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float2 *buf = smem + warp * kWarpBufElems;
-    float *tile = reinterpret_cast<float *>(buf);
-
-    const long long task = (long long)blockIdx.x * kWarpsPerCta + warp;
-    if (task >= p.n_tasks) return;  // warps are independent: no block-level barrier below
-    const long long b = task / p.tasks_per_clip;
-    const int q = (int)(task - b * p.tasks_per_clip);
-
-    const int Li = p.lengths ? min(p.lengths[b], p.L) : p.L;
-    const int Ti = p.lengths ? min(frames_of(Li, p.n_fft, p.hop, p.pad), p.T) : p.T;
-    const int t0 = kPair ? 2 * q : q;
-    const bool valid0 = t0 < Ti;
-    const bool valid1 = kPair && (t0 + 1 < Ti);
-    const float *row = p.wav + b * p.row_stride;
-
-    float2 a[32];
-
-    if (valid0) {
-        // ------------------------------------------------------------------ load + window
-        const int s0 = t0 * p.hop - p.pad;
-        if (kPair) {
-            const int s1 = s0 + p.hop;
-            const int last = valid1 ? s1 : s0;
-            const bool interior = (s0 >= 0) && (last + 1024 <= Li);
-            if (interior) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = 32 * j + lane;
-                    const float w = __ldg(p.window + n);
-                    a[j].x = __ldg(row + s0 + n) * w;
-                    a[j].y = valid1 ? __ldg(row + s1 + n) * w : 0.0f;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = 32 * j + lane;
-                    const float w = __ldg(p.window + n);
-                    a[j].x = __ldg(row + reflect_index(s0 + n, Li)) * w;
-                    a[j].y = valid1 ? __ldg(row + reflect_index(s1 + n, Li)) * w : 0.0f;
-                }
-            }
-        } else {
-            const bool interior = (s0 >= 0) && (s0 + 2048 <= Li);
-            if (interior) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = 64 * j + 2 * lane;
-                    a[j].x = __ldg(row + s0 + n) * __ldg(p.window + n);
-                    a[j].y = __ldg(row + s0 + n + 1) * __ldg(p.window + n + 1);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = 64 * j + 2 * lane;
-                    a[j].x = __ldg(row + reflect_index(s0 + n, Li)) * __ldg(p.window + n);
-                    a[j].y = __ldg(row + reflect_index(s0 + n + 1, Li)) * __ldg(p.window + n + 1);
-                }
-            }
-        }
-
-        // ------------------------------------------------------------------ 1024-point complex FFT
-        // pass 1: lane = n2, FFT over n1 -> Y[k1] at a[pos(k1)]
-        fft32(a);
-        // inter-pass twiddle W_1024^{n2 k1}, then transpose through shared memory
-        static_for<0, 32>([&](auto k1_) {
-            constexpr int k1 = decltype(k1_)::value;
-            float2 v = a[fft32_pos(k1)];
-            if constexpr (k1 > 0) v = cmul(v, __ldg(p.tw + k1 * 32 + lane));
-            buf[k1 * kBufStride + lane] = v;
-        });
-        __syncwarp();
-#pragma unroll
-        for (int n2 = 0; n2 < 32; ++n2) a[n2] = buf[lane * kBufStride + n2];
-        __syncwarp();  // buf is reused as the magnitude tile below
-        // pass 2: lane = k1, FFT over n2 -> Z[k1 + 32 k2] at a[pos(k2)]
-        fft32(a);
-
-        // ------------------------------------------------------------------ real-input separation
-        const int partner = (32 - lane) & 31;
-        float2 wl = make_float2(1.f, 0.f);
-        if (!kPair) wl = __ldg(p.tw_post + lane);
-        static_for<0, 16>([&](auto k2_) {
-            constexpr int k2 = decltype(k2_)::value;
-            const float2 A = a[fft32_pos(k2)];
-            // value my reader needs: lane 0 is read by itself and wants Z[32*((32-k2)&31)],
-            // lane s != 0 is read by lane 32-s which wants my slot 31-k2.
-            const float2 give0 = a[fft32_pos((32 - k2) & 31)];
-            const float2 give1 = a[fft32_pos(31 - k2)];
-            float2 give = lane == 0 ? give0 : give1;
-            float2 Bv;
-            Bv.x = __shfl_sync(0xffffffffu, give.x, partner);
-            Bv.y = __shfl_sync(0xffffffffu, give.y, partner);
-            const int k = lane + 32 * k2;
-            // E = A + conj(B), O = (A - conj(B)) / i   (the 1/2 is folded into the window)
-            const float2 E = make_float2(A.x + Bv.x, A.y - Bv.y);
-            const float2 O = make_float2(A.y + Bv.y, Bv.x - A.x);
-            if (kPair) {
-                const float m0 = magnitude(E.x, E.y, p), m1 = magnitude(O.x, O.y, p);
-                tile[k] = m0;
-                tile[kMagStride + k] = m1;
-                if (p.spec_kind) {
-                    store_spec(p, b, k, t0, E.x, E.y, m0);
-                    if (valid1) store_spec(p, b, k, t0 + 1, O.x, O.y, m1);
-                }
-            } else {
-                // X[k] = E + W_2048^k O,  X[1024-k] = conj(E - W_2048^k O),  W_2048^k = wl * W_64^{k2}
-                constexpr float w64c = TwConst::c64[k2], w64s = TwConst::s64[k2];
-                const float2 w64 = make_float2(w64c, w64s);
-                const float2 P = cmul(O, cmul(wl, w64));
-                const float2 X0 = cadd(E, P), X1 = csub(E, P);
-                const float m0 = magnitude(X0.x, X0.y, p), m1 = magnitude(X1.x, X1.y, p);
-                tile[k] = m0;
-                tile[1024 - k] = m1;
-                if (p.spec_kind) {
-                    store_spec(p, b, k, t0, X0.x, X0.y, m0);
-                    store_spec(p, b, 1024 - k, t0, X1.x, -X1.y, m1);
-                }
-            }
-        });
-        if (lane == 0) {  // bin 512 (k1 = 0, k2 = 16): its own partner
-            const float2 A = a[fft32_pos(16)];
-            if (kPair) {
-                const float re0 = 2.f * A.x, re1 = 2.f * A.y;
-                const float m0 = magnitude(re0, 0.f, p), m1 = magnitude(re1, 0.f, p);
-                tile[512] = m0;
-                tile[kMagStride + 512] = m1;
-                if (p.spec_kind) {
-                    store_spec(p, b, 512, t0, re0, 0.f, m0);
-                    if (valid1) store_spec(p, b, 512, t0 + 1, re1, 0.f, m1);
-                }
-            } else {  // E = 2 Re A, O = 2 Im A, W_2048^512 = -i  ->  X[512] = 2 (Re A - i Im A)
-                const float re = 2.f * A.x, im = -2.f * A.y;
-                const float m0 = magnitude(re, im, p);
-                tile[512] = m0;
-                if (p.spec_kind) store_spec(p, b, 512, t0, re, im, m0);
-            }
-        }
-        __syncwarp();
-    }
-
-    // ---------------------------------------------------------------------- frames past the clip's end
-    if (!valid0 || (kPair && !valid1)) {
-        // only reachable with `lengths` (or the odd last frame of a pair): zero-fill, as pad_collate_fn
-        // zero-pads per-item features (data/dataset.py:230-250).
-        const int tz0 = valid0 ? t0 + 1 : t0;
-        const int tz1 = kPair ? t0 + 1 : t0;
-        for (int t = tz0; t <= tz1 && t < p.T; ++t) {
-            if (p.out_mel)
-                for (int m = lane; m < p.n_mels; m += 32) p.out_mel[(b * p.n_mels + m) * (long long)p.T + t] = 0.f;
-            if (p.spec_kind)
-                for (int k = lane; k < p.n_freq; k += 32) {
-                    long long o = (b * p.n_freq + k) * (long long)p.T + t;
-                    p.out_a[o] = 0.f;
-                    if (p.spec_kind != B200MEL_SPEC_MAG) p.out_b[o] = 0.f;
-                }
-        }
-        if (!valid0) return;
-    }
-
-    // ---------------------------------------------------------------------- banded mel + log epilogue
-    if (p.out_mel) {
-        for (int m = lane; m < p.n_mels; m += 32) {
-            const int lo = __ldg(p.mel_lo + m), cnt = __ldg(p.mel_cnt + m);
-            const float *w = p.mel_w + __ldg(p.mel_ptr + m);
-            float acc0 = 0.f, acc1 = 0.f;
-            for (int j = 0; j < cnt; ++j) {
-                const float wj = __ldg(w + j);
-                acc0 = fmaf(wj, tile[lo + j], acc0);
-                if (kPair) acc1 = fmaf(wj, tile[kMagStride + lo + j], acc1);
-            }
-            float *o = p.out_mel + (b * p.n_mels + m) * (long long)p.T + t0;
-            o[0] = epilogue(acc0, p);
-            if (kPair && valid1) o[1] = epilogue(acc1, p);
-        }
-    }
-}
 
 // ----------------------------------------------------------------------------------------------
 // host side
@@ -361,31 +96,62 @@ using namespace b200mel;
 struct b200mel_plan {
     b200mel_config cfg;
     int device;
+    int num_sms;
     int pad, n_freq;
-    bool pair;
+    bool pair;        // n_fft == 1024: two frames per complex FFT
+    int pair_frames;  // frames per task (2 in pair mode unless hop > n_fft, else 1)
     // device tables
     float *d_window = nullptr;
     float2 *d_tw = nullptr, *d_tw_post = nullptr;
-    int *d_mel_lo = nullptr, *d_mel_cnt = nullptr, *d_mel_ptr = nullptr;
+    MelEntry *d_mel_entries = nullptr;
     float *d_mel_w = nullptr;
+    int mel_rounds = 0, mel_w_len = 0;
+    // shared-memory layout
+    int off_window = 0, off_entries = 0, off_melw = 0, off_bar = 0, off_regions = 0, region_bytes = 0, stage_bytes = 0;
+    int n_warps = 0, smem_bytes = 0;
     // staging for forward_host
     float *d_stage_in = nullptr, *d_stage_out = nullptr;
     size_t stage_in_bytes = 0, stage_out_bytes = 0;
 };
 
+constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
+
 static void free_mel_tables(b200mel_plan *pl) {
-    cudaFree(pl->d_mel_lo);
-    cudaFree(pl->d_mel_cnt);
-    cudaFree(pl->d_mel_ptr);
+    cudaFree(pl->d_mel_entries);
     cudaFree(pl->d_mel_w);
-    pl->d_mel_lo = pl->d_mel_cnt = pl->d_mel_ptr = nullptr;
+    pl->d_mel_entries = nullptr;
     pl->d_mel_w = nullptr;
+    pl->mel_rounds = pl->mel_w_len = 0;
 }
 
-// dense (n_mels x F) -> banded rows [lo, lo+cnt) and upload
+// Shared-memory carve-up (must match logmel_kernel.cuh): tw | window | mel entries | mel weights | mbarriers | warp regions
+static int layout_smem(b200mel_plan *pl) {
+    const int n_fft = pl->cfg.n_fft;
+    const int span = n_fft + (pl->pair_frames == 2 ? pl->cfg.hop_length : 0);
+    pl->stage_bytes = ((span + 8) * 4 + 15) & ~15;
+    int region = kStageOff + pl->stage_bytes;
+    if (region < kXposeBytes) region = kXposeBytes;
+    pl->region_bytes = (region + 127) & ~127;
+    pl->off_window = 32 * 32 * 8;
+    pl->off_entries = pl->off_window + n_fft * 4;
+    pl->off_melw = pl->off_entries + pl->mel_rounds * 32 * (int)sizeof(MelEntry);
+    pl->off_bar = pl->off_melw + pl->mel_w_len * 4;
+    pl->off_regions = (pl->off_bar + kMaxWarps * 8 + 127) & ~127;
+    int n_warps = (kMaxSmem - pl->off_regions) / pl->region_bytes;
+    if (n_warps > kMaxWarps) n_warps = kMaxWarps;
+    if (n_warps < 1)
+        return fail(B200MEL_EUNSUP, "plan: hop_length / filterbank too large for the shared-memory staging of this build");
+    pl->n_warps = n_warps;
+    pl->smem_bytes = pl->off_regions + n_warps * pl->region_bytes;
+    return B200MEL_OK;
+}
+
+// dense (n_mels x F) -> lane-balanced banded schedule and upload.
+// Rows are cut to [first non-zero, last non-zero], padded with zero weights to a multiple of 4, sorted by
+// padded length (longest first) and dealt 32 per round, so the lanes of a warp run rows of similar length.
 static int upload_filterbank(b200mel_plan *pl, const float *W, int n_mels, int F) {
-    std::vector<int> lo(n_mels), cnt(n_mels), ptr(n_mels);
-    std::vector<float> w;
+    struct Row { int m, lo, cnt; };
+    std::vector<Row> rows(n_mels);
     for (int m = 0; m < n_mels; ++m) {
         int first = -1, last = -1;
         for (int k = 0; k < F; ++k)
@@ -393,24 +159,42 @@ static int upload_filterbank(b200mel_plan *pl, const float *W, int n_mels, int F
                 if (first < 0) first = k;
                 last = k;
             }
-        lo[m] = first < 0 ? 0 : first;
-        cnt[m] = first < 0 ? 0 : last - first + 1;
-        ptr[m] = (int)w.size();
-        for (int k = 0; k < cnt[m]; ++k) w.push_back(W[(size_t)m * F + lo[m] + k]);
+        rows[m] = {m, first < 0 ? 0 : first, first < 0 ? 0 : last - first + 1};
     }
-    if (w.empty()) w.push_back(0.f);
+    std::stable_sort(rows.begin(), rows.end(), [](const Row &x, const Row &y) { return x.cnt > y.cnt; });
+    const int rounds = (n_mels + 31) / 32;
+    std::vector<MelEntry> ent((size_t)rounds * 32, MelEntry{0, 0, 0, -1});
+    std::vector<float> w;
+    for (int i = 0; i < n_mels; ++i) {
+        const Row &r = rows[i];
+        const int groups = (r.cnt + 3) / 4;
+        ent[i] = MelEntry{r.lo, groups, (int)w.size(), r.m};
+        for (int k = 0; k < groups * 4; ++k) w.push_back(k < r.cnt ? W[(size_t)r.m * F + r.lo + k] : 0.f);
+    }
+    if (w.empty()) w.resize(4, 0.f);
     free_mel_tables(pl);
     cudaError_t e;
-    if ((e = cudaMalloc(&pl->d_mel_lo, n_mels * sizeof(int))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
-    if ((e = cudaMalloc(&pl->d_mel_cnt, n_mels * sizeof(int))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
-    if ((e = cudaMalloc(&pl->d_mel_ptr, n_mels * sizeof(int))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&pl->d_mel_entries, ent.size() * sizeof(MelEntry))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
     if ((e = cudaMalloc(&pl->d_mel_w, w.size() * sizeof(float))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
-    cudaMemcpy(pl->d_mel_lo, lo.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice);
-    cudaMemcpy(pl->d_mel_cnt, cnt.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice);
-    cudaMemcpy(pl->d_mel_ptr, ptr.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(pl->d_mel_entries, ent.data(), ent.size() * sizeof(MelEntry), cudaMemcpyHostToDevice);
     e = cudaMemcpy(pl->d_mel_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(filterbank)");
-    return B200MEL_OK;
+    pl->mel_rounds = rounds;
+    pl->mel_w_len = (int)w.size();
+    return layout_smem(pl);
+}
+
+typedef void (*kernel_fn)(const KParams);
+static kernel_fn pick_kernel(bool pair, int spec, bool mel, int power) {
+    if (mel) {
+        if (pair) return power == 2 ? logmel_kernel<true, 0, true, 2> : logmel_kernel<true, 0, true, 1>;
+        return power == 2 ? logmel_kernel<false, 0, true, 2> : logmel_kernel<false, 0, true, 1>;
+    }
+    switch (spec) {
+        case B200MEL_SPEC_MAG_PHASE: return pair ? logmel_kernel<true, 1, false, 1> : logmel_kernel<false, 1, false, 1>;
+        case B200MEL_SPEC_RE_IM: return pair ? logmel_kernel<true, 2, false, 1> : logmel_kernel<false, 2, false, 1>;
+        default: return pair ? logmel_kernel<true, 3, false, 1> : logmel_kernel<false, 3, false, 1>;
+    }
 }
 
 extern "C" {
@@ -481,7 +265,9 @@ int b200mel_plan_create(const b200mel_config *cfg, b200mel_plan **out) {
     if (!pl) return fail(B200MEL_ENOMEM, "plan_create: out of host memory");
     pl->cfg = *cfg;
     pl->device = dev;
+    pl->num_sms = prop.multiProcessorCount;
     pl->pair = cfg->n_fft == 1024;
+    pl->pair_frames = (pl->pair && cfg->hop_length <= cfg->n_fft) ? 2 : 1;
     pl->n_freq = cfg->n_fft / 2 + 1;
     pl->pad = cfg->pad_mode == B200MEL_PAD_CENTER ? cfg->n_fft / 2 : (cfg->n_fft - cfg->hop_length) / 2;
     if (pl->pad < 0) pl->pad = 0;
@@ -516,11 +302,14 @@ int b200mel_plan_create(const b200mel_config *cfg, b200mel_plan **out) {
                              cfg->mel_norm == B200MEL_NORM_SLANEY, W.data());
             rc = upload_filterbank(pl, W.data(), cfg->n_mels, pl->n_freq);
             if (rc) break;
-        }
-        const int smem = kWarpsPerCta * kWarpBufElems * (int)sizeof(float2);
-        e = cudaFuncSetAttribute(logmel_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(logmel_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        } else if ((rc = layout_smem(pl)) != B200MEL_OK)
+            break;
+        for (int spec = 0; spec <= 3 && e == cudaSuccess; ++spec)
+            for (int power = 1; power <= 2 && e == cudaSuccess; ++power) {
+                if (spec != 0 && power == 2) continue;
+                e = cudaFuncSetAttribute(pick_kernel(pl->pair, spec, spec == 0, power),
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+            }
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute (is the library built for this GPU?)"); break; }
     } while (0);
     if (rc) {
@@ -596,21 +385,27 @@ int b200mel_forward(const b200mel_plan *pl, const float *wav, int64_t B, int64_t
     p.hop = pl->cfg.hop_length;
     p.pad = pl->pad;
     p.n_fft = pl->cfg.n_fft;
+    p.pair_frames = pl->pair_frames;
     p.window = pl->d_window;
     p.tw = pl->d_tw;
     p.tw_post = pl->d_tw_post;
+    p.mel_entries = pl->d_mel_entries;
+    p.mel_w = pl->d_mel_w;
     p.n_mels = pl->cfg.n_mels;
     p.n_freq = pl->n_freq;
-    p.mel_lo = pl->d_mel_lo;
-    p.mel_cnt = pl->d_mel_cnt;
-    p.mel_ptr = pl->d_mel_ptr;
-    p.mel_w = pl->d_mel_w;
+    p.mel_rounds = pl->mel_rounds;
+    p.mel_w_len = pl->mel_w_len;
+    p.off_window = pl->off_window;
+    p.off_entries = pl->off_entries;
+    p.off_melw = pl->off_melw;
+    p.off_bar = pl->off_bar;
+    p.off_regions = pl->off_regions;
+    p.region_bytes = pl->region_bytes;
+    p.stage_bytes = pl->stage_bytes;
     p.out_mel = out_mel;
     p.out_a = out_a;
     p.out_b = out_b;
-    p.spec_kind = spec_kind;
     p.mag_eps = pl->cfg.mag_eps;
-    p.power = pl->cfg.power;
     if (epi) {
         p.log_kind = epi->log_kind;
         p.log_arg = epi->log_arg;
@@ -621,18 +416,21 @@ int b200mel_forward(const b200mel_plan *pl, const float *wav, int64_t B, int64_t
         p.norm = epi->norm_mel;
         if (p.norm) p.norm_scale = 2.0f / (p.hi - p.lo);
     }
-    p.tasks_per_clip = pl->pair ? (T + 1) / 2 : T;
+    p.tasks_per_clip = (T + pl->pair_frames - 1) / pl->pair_frames;
     p.n_tasks = p.tasks_per_clip * B;
-    const long long n_cta = (p.n_tasks + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (n_cta > 0x7fffffffLL) return fail(B200MEL_EINVAL, "forward: batch too large for one launch");
+    long long n_cta = (p.n_tasks + pl->n_warps - 1) / pl->n_warps;
+    if (n_cta > pl->num_sms) n_cta = pl->num_sms;  // persistent: one CTA per SM, warps stride over the tasks
 
-    const int smem = kWarpsPerCta * kWarpBufElems * (int)sizeof(float2);
     cudaStream_t st = (cudaStream_t)stream;
-    if (pl->pair)
-        logmel_warp_kernel<true><<<(unsigned)n_cta, kWarpsPerCta * 32, smem, st>>>(p);
-    else
-        logmel_warp_kernel<false><<<(unsigned)n_cta, kWarpsPerCta * 32, smem, st>>>(p);
-    g_launches.fetch_add(1);
+    // mel and spectrum outputs come from separately specialised kernels (no reference module needs both at once)
+    if (out_mel) {
+        pick_kernel(pl->pair, 0, true, pl->cfg.power)<<<(unsigned)n_cta, pl->n_warps * 32, pl->smem_bytes, st>>>(p);
+        g_launches.fetch_add(1);
+    }
+    if (spec_kind) {
+        pick_kernel(pl->pair, spec_kind, false, 1)<<<(unsigned)n_cta, pl->n_warps * 32, pl->smem_bytes, st>>>(p);
+        g_launches.fetch_add(1);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     return B200MEL_OK;

@@ -1,0 +1,479 @@
+// logmel_kernel.cuh — the fused STFT -> |.| -> mel -> log kernel (sm_100a), v2.
+//
+// Persistent grid: one CTA per SM, up to 16 warps per CTA, every warp an independent pipeline that
+// walks the task list with stride (#warps in the grid).  A task is one 1024-point complex FFT held in
+// registers (32 complex values per lane, two radix-32 passes, one shared-memory transpose):
+//   kPair  (n_fft = 1024): frames (2q, 2q+1) of a clip packed as re/im, separated by conjugate symmetry;
+//   !kPair (n_fft = 2048): frame q packed even/odd, finished by the real-input split pass.
+//
+// Per-warp shared-memory region (bytes):
+//   [0, 4160)              magnitude tile   (pair: float2[520] = {|X_t[k]|, |X_t+1[k]|}; split: float[1032])
+//   [4224, 4224 + stage)   sample stage     (filled by ONE cp.async.bulk = TMA 1-D copy per task, mbarrier-signalled)
+//   [0, 8448)              transpose buffer (float2[32][33]) — overlaps both, live only between the two
+//                          radix-32 passes, i.e. after the stage was consumed and before the next TMA is issued.
+// The TMA for task i+1 is issued right after the transpose of task i, so the copy lands while the warp
+// does its second FFT pass, the separation, the mel contraction and the epilogue of task i.
+//
+// CTA-shared tables (loaded once per CTA): inter-pass twiddles, window, banded mel filterbank in a
+// lane-balanced schedule (rows sorted by length, 32 rows per round, weights padded to float4 groups).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200mel.h"
+#include "fft32.cuh"
+
+namespace b200mel {
+
+constexpr int kMaxWarps = 16;
+constexpr int kBufStride = 33;                           // float2 per transposed row (+1 pad)
+constexpr int kXposeBytes = 32 * kBufStride * 8;          // 8448
+constexpr int kTileBytes = 4160;                          // magnitude tile
+constexpr int kStageOff = 4224;                           // stage offset inside the warp region (128B aligned)
+constexpr int kPairTileLen = 520;                         // float2 entries (513 used, tail zeroed)
+constexpr int kSplitTileLen = 1032;                       // float entries (1025 used, tail zeroed)
+
+struct MelEntry {  // one filterbank row as seen by one lane in one round
+    int lo;        // first spectrum bin
+    int groups;    // number of float4 weight groups (row length padded to a multiple of 4 with zeros)
+    int woff;      // float offset of the row's weights in the shared weight array (multiple of 4)
+    int m;         // mel row index, -1 = idle lane
+};
+
+struct KParams {
+    const float *wav;
+    long long row_stride;
+    long long B;
+    int L;
+    const int *lengths;
+    int T, hop, pad, n_fft;
+    int pair_frames;  // frames per task: 2 (pair mode) or 1 (split mode, or pair mode with hop > n_fft)
+    // global copies of the CTA tables
+    const float *window;    // [n_fft], periodic Hann centre-padded, pre-scaled by 0.5
+    const float2 *tw;       // [32][32]  tw[k1*32 + lane] = exp(-2 pi i k1 lane / 1024)
+    const float2 *tw_post;  // [32]      exp(-2 pi i lane / 2048)            (split mode)
+    const MelEntry *mel_entries;  // [rounds][32]
+    const float *mel_w;           // [mel_w_len]
+    int n_mels, n_freq, mel_rounds, mel_w_len;
+    // shared memory layout (bytes from the dynamic smem base)
+    int off_window, off_entries, off_melw, off_bar, off_regions, region_bytes, stage_bytes;
+    // outputs
+    float *out_mel, *out_a, *out_b;
+    float mag_eps;
+    int log_kind;
+    float log_arg;
+    int has_lo, has_hi, norm;
+    float lo, hi, norm_scale;
+    long long tasks_per_clip, n_tasks;
+};
+
+// ------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // one MUFU.SQRT, max rel. error 2^-23
+    return y;
+}
+
+// ln / log10 through one MUFU.LG2 (abs. error ~1e-6 on the log value, two orders below the 1e-4 tolerance)
+__device__ __forceinline__ float fast_ln(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y * 0.693147180559945309f;
+}
+__device__ __forceinline__ float fast_log10(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y * 0.301029995663981195f;
+}
+
+__device__ __forceinline__ int frames_of(int Li, int n_fft, int hop, int pad) {
+    int span = Li + 2 * pad - n_fft;
+    return span < 0 ? 0 : span / hop + 1;
+}
+__device__ __forceinline__ int reflect_index(int i, int Li) {
+    if (i < 0) i = -i;
+    if (i >= Li) i = 2 * (Li - 1) - i;
+    return min(max(i, 0), Li - 1);
+}
+
+__device__ __forceinline__ float epilogue(float x, const KParams &p) {
+    float y = x;
+    if (p.log_kind == B200MEL_LOG_LN_OFFSET)
+        y = fast_ln(x + p.log_arg);
+    else if (p.log_kind == B200MEL_LOG_LN_FLOOR)
+        y = fast_ln(fmaxf(x, p.log_arg));
+    else if (p.log_kind == B200MEL_LOG_LOG10_FLOOR)
+        y = fast_log10(fmaxf(x, p.log_arg));
+    if (p.has_lo) y = fmaxf(y, p.lo);
+    if (p.has_hi) y = fminf(y, p.hi);
+    if (p.norm) y = (y - p.lo) * p.norm_scale - 1.0f;
+    return y;
+}
+
+template <int kPower>
+__device__ __forceinline__ float magnitude(float re, float im, float eps) {
+    const float sq = fmaf(re, re, im * im);
+    if constexpr (kPower == 2) return sq;
+    return sqrt_approx(sq + eps);
+}
+
+// Everything that locates a task; recomputed identically by the prefetch and the consume side.
+struct Task {
+    long long b;
+    int t0, Li, s_first;  // first frame, clip length, first padded-coordinate sample of the span
+    bool valid0, valid1;
+    int span;             // samples staged: n_fft (+ hop when the second frame is valid)
+};
+
+template <bool kPair>
+__device__ __forceinline__ Task decode_task(const KParams &p, long long task) {
+    Task t;
+    t.b = task / p.tasks_per_clip;
+    const int q = (int)(task - t.b * p.tasks_per_clip);
+    t.Li = p.lengths ? min(__ldg(p.lengths + t.b), p.L) : p.L;
+    const int Ti = p.lengths ? min(frames_of(t.Li, p.n_fft, p.hop, p.pad), p.T) : p.T;
+    t.t0 = q * p.pair_frames;
+    t.valid0 = t.t0 < Ti;
+    t.valid1 = kPair && p.pair_frames == 2 && (t.t0 + 1 < Ti);
+    t.s_first = t.t0 * p.hop - p.pad;
+    t.span = p.n_fft + (t.valid1 ? p.hop : 0);
+    return t;
+}
+
+// Stage index of padded-coordinate sample position `s` is (s - s_first + delta): delta in 0..3 makes the first
+// in-range sample land 16-byte-congruent with its global address, as the bulk copy requires.
+__device__ __forceinline__ int stage_delta(const float *row, const Task &t) {
+    const int p_lo = max(t.s_first, 0);
+    return (int)(((reinterpret_cast<uintptr_t>(row + p_lo) >> 2) - (uintptr_t)(p_lo - t.s_first)) & 3);
+}
+
+// One elected lane: arm the warp's mbarrier and issue the bulk copy of the in-range part of the span.
+// The copy is widened to 16-byte boundaries on both sides (the extra <= 3 floats on each side are never read
+// as samples: interior tasks ignore them, edge tasks overwrite the halo after the copy has landed).
+template <bool kPair>
+__device__ __forceinline__ void issue_stage(const KParams &p, const Task &t, float *stage, uint32_t bar) {
+    const float *row = p.wav + t.b * p.row_stride;
+    const int p_lo = max(t.s_first, 0), p_hi = min(t.s_first + t.span, t.Li);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(row + p_lo), e = reinterpret_cast<uintptr_t>(row + p_hi);
+    const uintptr_t a16 = a & ~(uintptr_t)15, e16 = (e + 15) & ~(uintptr_t)15;
+    const int delta = stage_delta(row, t);
+    const int idx_lo = p_lo - t.s_first + delta;              // stage index of sample p_lo
+    float *dst = stage + (idx_lo - (int)((a >> 2) & 3));      // multiple of 4 floats by construction
+    const uint32_t bytes = (uint32_t)(e16 - a16);
+    fence_proxy_async();
+    mbar_arrive_expect_tx(bar, bytes);
+    tma_load_1d(smem_u32(dst), reinterpret_cast<const void *>(a16), bytes, bar);
+}
+
+// kSpec: B200MEL_SPEC_* ; kMel: apply the filterbank + epilogue ; kPower: 1 magnitude, 2 power
+template <bool kPair, int kSpec, bool kMel, int kPower>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_warps = blockDim.x >> 5;
+
+    // ------------------------------------------------------------------ CTA tables -> shared memory
+    float2 *s_tw = reinterpret_cast<float2 *>(smem_raw);
+    float *s_win = reinterpret_cast<float *>(smem_raw + p.off_window);
+    const MelEntry *s_ent = reinterpret_cast<const MelEntry *>(smem_raw + p.off_entries);
+    const float *s_melw = reinterpret_cast<const float *>(smem_raw + p.off_melw);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + p.off_bar);
+    {
+        const int4 *g;
+        int4 *s;
+        g = reinterpret_cast<const int4 *>(p.tw);
+        s = reinterpret_cast<int4 *>(s_tw);
+        for (int i = threadIdx.x; i < 32 * 32 * 8 / 16; i += blockDim.x) s[i] = __ldg(g + i);
+        g = reinterpret_cast<const int4 *>(p.window);
+        s = reinterpret_cast<int4 *>(s_win);
+        for (int i = threadIdx.x; i < p.n_fft / 4; i += blockDim.x) s[i] = __ldg(g + i);
+        if (kMel) {
+            g = reinterpret_cast<const int4 *>(p.mel_entries);
+            s = reinterpret_cast<int4 *>(smem_raw + p.off_entries);
+            for (int i = threadIdx.x; i < p.mel_rounds * 32; i += blockDim.x) s[i] = __ldg(g + i);
+            g = reinterpret_cast<const int4 *>(p.mel_w);
+            s = reinterpret_cast<int4 *>(smem_raw + p.off_melw);
+            for (int i = threadIdx.x; i < p.mel_w_len / 4; i += blockDim.x) s[i] = __ldg(g + i);
+        }
+        if (threadIdx.x < n_warps) mbar_init(smem_u32(s_bar + threadIdx.x), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();  // the only block-wide barrier; warps are independent from here on
+
+    unsigned char *region = smem_raw + p.off_regions + warp * p.region_bytes;
+    float2 *buf = reinterpret_cast<float2 *>(region);          // transpose buffer
+    float2 *tile2 = reinterpret_cast<float2 *>(region);        // pair-mode magnitude tile
+    float *tile1 = reinterpret_cast<float *>(region);          // split-mode magnitude tile
+    float *stage = reinterpret_cast<float *>(region + kStageOff);
+    const uint32_t bar = smem_u32(s_bar + warp);
+    uint32_t parity = 0;
+
+    const long long stride = (long long)gridDim.x * n_warps;
+    long long task = (long long)blockIdx.x * n_warps + warp;
+
+    float2 wl = make_float2(1.f, 0.f);
+    if (!kPair) wl = __ldg(p.tw_post + lane);
+
+    if (task < p.n_tasks && lane == 0) {
+        const Task t = decode_task<kPair>(p, task);
+        if (t.valid0) issue_stage<kPair>(p, t, stage, bar);
+    }
+
+    for (; task < p.n_tasks; task += stride) {
+        const Task t = decode_task<kPair>(p, task);
+        const long long b = t.b;
+        const int t0 = t.t0;
+        float2 a[32];
+
+        if (t.valid0) {
+            const float *row = p.wav + b * p.row_stride;
+            const int delta = stage_delta(row, t);
+            mbar_wait(bar, parity);
+            parity ^= 1;
+            // -------------------------------------------------------------- halo (reflect) fix-up, edge tasks only
+            if (t.s_first < 0 || t.s_first + t.span > t.Li) {
+                for (int i = lane; i < t.span; i += 32) {
+                    const int s = t.s_first + i;
+                    if (s < 0 || s >= t.Li) stage[i + delta] = __ldg(row + reflect_index(s, t.Li));
+                }
+                __syncwarp();
+            }
+            // -------------------------------------------------------------- stage -> registers, windowed
+            const float *x0 = stage + delta + lane;
+            if (kPair) {
+                if (t.valid1) {
+                    const float *x1 = x0 + p.hop;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float w = s_win[32 * j + lane];
+                        a[j].x = x0[32 * j] * w;
+                        a[j].y = x1[32 * j] * w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        a[j].x = x0[32 * j] * s_win[32 * j + lane];
+                        a[j].y = 0.f;
+                    }
+                }
+            } else {
+                const float2 *w2 = reinterpret_cast<const float2 *>(s_win);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float2 w = w2[32 * j + lane];
+                    a[j].x = x0[64 * j + lane] * w.x;        // sample 64 j + 2 lane
+                    a[j].y = x0[64 * j + lane + 1] * w.y;    // sample 64 j + 2 lane + 1
+                }
+            }
+
+            // -------------------------------------------------------------- 1024-point complex FFT
+            fft32(a);  // pass 1: lane = n2, FFT over n1 -> Y[k1] at a[pos(k1)]
+            __syncwarp();  // every lane has consumed the stage before the transpose buffer overwrites it
+            static_for<0, 32>([&](auto k1_) {
+                constexpr int k1 = decltype(k1_)::value;
+                float2 v = a[fft32_pos(k1)];
+                if constexpr (k1 > 0) v = cmul(v, s_tw[k1 * 32 + lane]);
+                buf[k1 * kBufStride + lane] = v;
+            });
+            __syncwarp();
+#pragma unroll
+            for (int n2 = 0; n2 < 32; ++n2) a[n2] = buf[lane * kBufStride + n2];
+            __syncwarp();  // transpose buffer is dead: magnitude tile and next stage may reuse it
+        }
+
+        // ------------------------------------------------------------------ prefetch the next task's samples
+        {
+            const long long nt = task + stride;
+            if (nt < p.n_tasks && lane == 0) {
+                const Task n = decode_task<kPair>(p, nt);
+                if (n.valid0) issue_stage<kPair>(p, n, stage, bar);
+            }
+        }
+
+        if (t.valid0) {
+            fft32(a);  // pass 2: lane = k1, FFT over n2 -> Z[k1 + 32 k2] at a[pos(k2)]
+
+            // -------------------------------------------------------------- real-input separation + magnitudes
+            const int partner = (32 - lane) & 31;
+            static_for<0, 16>([&](auto k2_) {
+                constexpr int k2 = decltype(k2_)::value;
+                const float2 A = a[fft32_pos(k2)];
+                // value my reader needs: lane 0 is read by itself and wants Z[32*((32-k2)&31)];
+                // lane s != 0 is read by lane 32-s, which wants my slot 31-k2.
+                const float2 g0 = a[fft32_pos((32 - k2) & 31)];
+                const float2 g1 = a[fft32_pos(31 - k2)];
+                float2 Bv;
+                Bv.x = __shfl_sync(0xffffffffu, lane == 0 ? g0.x : g1.x, partner);
+                Bv.y = __shfl_sync(0xffffffffu, lane == 0 ? g0.y : g1.y, partner);
+                const int k = lane + 32 * k2;
+                // E = A + conj(B), O = (A - conj(B)) / i   (the 1/2 is folded into the window)
+                const float2 E = make_float2(A.x + Bv.x, A.y - Bv.y);
+                const float2 O = make_float2(A.y + Bv.y, Bv.x - A.x);
+                if constexpr (kPair) {
+                    const float m0 = magnitude<kPower>(E.x, E.y, p.mag_eps);
+                    const float m1 = magnitude<kPower>(O.x, O.y, p.mag_eps);
+                    if constexpr (kMel) tile2[k] = make_float2(m0, m1);
+                    if constexpr (kSpec != B200MEL_SPEC_NONE) {
+                        const long long o = (b * p.n_freq + k) * (long long)p.T + t0;
+                        if constexpr (kSpec == B200MEL_SPEC_RE_IM) {
+                            p.out_a[o] = E.x;
+                            p.out_b[o] = E.y;
+                            if (t.valid1) p.out_a[o + 1] = O.x, p.out_b[o + 1] = O.y;
+                        } else {
+                            p.out_a[o] = m0;
+                            if (t.valid1) p.out_a[o + 1] = m1;
+                            if constexpr (kSpec == B200MEL_SPEC_MAG_PHASE) {
+                                p.out_b[o] = atan2f(E.y, E.x);
+                                if (t.valid1) p.out_b[o + 1] = atan2f(O.y, O.x);
+                            }
+                        }
+                    }
+                } else {
+                    // X[k] = E + W_2048^k O,  X[1024-k] = conj(E - W_2048^k O),  W_2048^k = wl * W_64^{k2}
+                    constexpr float w64c = TwConst::c64[k2], w64s = TwConst::s64[k2];
+                    const float2 P = cmul(O, cmul(wl, make_float2(w64c, w64s)));
+                    const float2 X0 = cadd(E, P), X1 = csub(E, P);
+                    const float m0 = magnitude<kPower>(X0.x, X0.y, p.mag_eps);
+                    const float m1 = magnitude<kPower>(X1.x, X1.y, p.mag_eps);
+                    if constexpr (kMel) {
+                        tile1[k] = m0;
+                        tile1[1024 - k] = m1;
+                    }
+                    if constexpr (kSpec != B200MEL_SPEC_NONE) {
+                        const long long o0 = (b * p.n_freq + k) * (long long)p.T + t0;
+                        const long long o1 = (b * p.n_freq + (1024 - k)) * (long long)p.T + t0;
+                        if constexpr (kSpec == B200MEL_SPEC_RE_IM) {
+                            p.out_a[o0] = X0.x, p.out_b[o0] = X0.y;
+                            p.out_a[o1] = X1.x, p.out_b[o1] = -X1.y;
+                        } else {
+                            p.out_a[o0] = m0, p.out_a[o1] = m1;
+                            if constexpr (kSpec == B200MEL_SPEC_MAG_PHASE) {
+                                p.out_b[o0] = atan2f(X0.y, X0.x);
+                                p.out_b[o1] = atan2f(-X1.y, X1.x);
+                            }
+                        }
+                    }
+                }
+            });
+            if (lane == 0) {  // bin 512 (k1 = 0, k2 = 16) is its own partner
+                const float2 A = a[fft32_pos(16)];
+                float re0, im0, re1 = 0.f;
+                if constexpr (kPair) {
+                    re0 = 2.f * A.x, im0 = 0.f, re1 = 2.f * A.y;
+                } else {  // E = 2 Re A, O = 2 Im A, W_2048^512 = -i  ->  X[512] = 2 (Re A - i Im A)
+                    re0 = 2.f * A.x, im0 = -2.f * A.y;
+                }
+                const float m0 = magnitude<kPower>(re0, im0, p.mag_eps);
+                const float m1 = magnitude<kPower>(re1, 0.f, p.mag_eps);
+                if constexpr (kMel) {
+                    if constexpr (kPair) tile2[512] = make_float2(m0, m1);
+                    else tile1[512] = m0;
+                }
+                if constexpr (kSpec != B200MEL_SPEC_NONE) {
+                    const long long o = (b * p.n_freq + 512) * (long long)p.T + t0;
+                    if constexpr (kSpec == B200MEL_SPEC_RE_IM) {
+                        p.out_a[o] = re0, p.out_b[o] = im0;
+                        if (kPair && t.valid1) p.out_a[o + 1] = re1, p.out_b[o + 1] = 0.f;
+                    } else {
+                        p.out_a[o] = m0;
+                        if (kPair && t.valid1) p.out_a[o + 1] = m1;
+                        if constexpr (kSpec == B200MEL_SPEC_MAG_PHASE) {
+                            p.out_b[o] = atan2f(im0, re0);
+                            if (kPair && t.valid1) p.out_b[o + 1] = atan2f(0.f, re1);
+                        }
+                    }
+                }
+            }
+            if constexpr (kMel) {  // zero the padded tail the float4 weight groups may touch
+                if (lane < 7) {
+                    if constexpr (kPair) tile2[513 + lane] = make_float2(0.f, 0.f);
+                    else tile1[1025 + lane] = 0.f;
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---------------------------------------------------------------------- frames past the clip's end
+        if (!t.valid0 || (kPair && p.pair_frames == 2 && !t.valid1)) {
+            // only with `lengths` (or the odd last frame of a pair): zero-fill, as pad_collate_fn zero-pads
+            // per-item features (data/dataset.py:230-250).
+            const int tz0 = t.valid0 ? t0 + 1 : t0;
+            const int tz1 = t0 + p.pair_frames - 1;
+            for (int tt = tz0; tt <= tz1 && tt < p.T; ++tt) {
+                if (kMel)
+                    for (int m = lane; m < p.n_mels; m += 32) p.out_mel[(b * p.n_mels + m) * (long long)p.T + tt] = 0.f;
+                if (kSpec != B200MEL_SPEC_NONE)
+                    for (int k = lane; k < p.n_freq; k += 32) {
+                        const long long o = (b * p.n_freq + k) * (long long)p.T + tt;
+                        p.out_a[o] = 0.f;
+                        if (kSpec != B200MEL_SPEC_MAG) p.out_b[o] = 0.f;
+                    }
+            }
+            if (!t.valid0) continue;
+        }
+
+        // ---------------------------------------------------------------------- banded mel + log epilogue
+        if constexpr (kMel) {
+            for (int r = 0; r < p.mel_rounds; ++r) {
+                const MelEntry e = s_ent[r * 32 + lane];
+                const float4 *w4 = reinterpret_cast<const float4 *>(s_melw + e.woff);
+                float acc0 = 0.f, acc1 = 0.f;
+                if constexpr (kPair) {
+                    const float2 *mg = tile2 + e.lo;
+                    for (int g = 0; g < e.groups; ++g) {
+                        const float4 w = w4[g];
+                        const float2 v0 = mg[4 * g], v1 = mg[4 * g + 1], v2 = mg[4 * g + 2], v3 = mg[4 * g + 3];
+                        acc0 = fmaf(w.x, v0.x, acc0), acc1 = fmaf(w.x, v0.y, acc1);
+                        acc0 = fmaf(w.y, v1.x, acc0), acc1 = fmaf(w.y, v1.y, acc1);
+                        acc0 = fmaf(w.z, v2.x, acc0), acc1 = fmaf(w.z, v2.y, acc1);
+                        acc0 = fmaf(w.w, v3.x, acc0), acc1 = fmaf(w.w, v3.y, acc1);
+                    }
+                } else {
+                    const float *mg = tile1 + e.lo;
+                    for (int g = 0; g < e.groups; ++g) {
+                        const float4 w = w4[g];
+                        acc0 = fmaf(w.x, mg[4 * g], acc0);
+                        acc0 = fmaf(w.y, mg[4 * g + 1], acc0);
+                        acc0 = fmaf(w.z, mg[4 * g + 2], acc0);
+                        acc0 = fmaf(w.w, mg[4 * g + 3], acc0);
+                    }
+                }
+                if (e.m >= 0) {
+                    float *o = p.out_mel + (b * p.n_mels + e.m) * (long long)p.T + t0;
+                    o[0] = epilogue(acc0, p);
+                    if (kPair && t.valid1) o[1] = epilogue(acc1, p);
+                }
+            }
+            __syncwarp();  // tile reads done before the next task's transpose overwrites the region
+        }
+    }
+}
+
+}  // namespace b200mel
