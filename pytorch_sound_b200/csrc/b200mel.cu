@@ -12,6 +12,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -106,6 +107,7 @@ struct b200mel_plan {
     MelEntry *d_mel_entries = nullptr;
     float *d_mel_w = nullptr;
     int mel_rounds = 0, mel_w_len = 0;
+    int round_groups[kMaxMelRounds] = {0}, round_wbase[kMaxMelRounds] = {0};
     // shared-memory layout
     int off_window = 0, off_entries = 0, off_melw = 0, off_bar = 0, off_regions = 0, region_bytes = 0, stage_bytes = 0;
     int n_warps = 0, smem_bytes = 0;
@@ -114,7 +116,8 @@ struct b200mel_plan {
     size_t stage_in_bytes = 0, stage_out_bytes = 0;
 };
 
-constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
+constexpr int kMaxSmem = 232448;
+constexpr int kDefaultWarps = 16;  // 227 KB opt-in limit per CTA on sm_100
 
 static void free_mel_tables(b200mel_plan *pl) {
     cudaFree(pl->d_mel_entries);
@@ -138,7 +141,11 @@ static int layout_smem(b200mel_plan *pl) {
     pl->off_bar = pl->off_melw + pl->mel_w_len * 4;
     pl->off_regions = (pl->off_bar + kMaxWarps * 8 + 127) & ~127;
     int n_warps = (kMaxSmem - pl->off_regions) / pl->region_bytes;
-    if (n_warps > kMaxWarps) n_warps = kMaxWarps;
+    int cap = kDefaultWarps;
+    if (const char *env = getenv("B200MEL_WARPS")) cap = atoi(env);  // tuning knob: 16, 20 or 24
+    if (cap < 1) cap = 1;
+    if (cap > kMaxWarps) cap = kMaxWarps;
+    if (n_warps > cap) n_warps = cap;
     if (n_warps < 1)
         return fail(B200MEL_EUNSUP, "plan: hop_length / filterbank too large for the shared-memory staging of this build");
     pl->n_warps = n_warps;
@@ -146,11 +153,20 @@ static int layout_smem(b200mel_plan *pl) {
     return B200MEL_OK;
 }
 
-// dense (n_mels x F) -> lane-balanced banded schedule and upload.
-// Rows are cut to [first non-zero, last non-zero], padded with zero weights to a multiple of 4, sorted by
-// padded length (longest first) and dealt 32 per round, so the lanes of a warp run rows of similar length.
+// dense (n_mels x F) -> lane-balanced, bank-conflict-free banded schedule, uploaded to the device.
+//
+// Rows are cut to [first non-zero, last non-zero] and sorted by length (longest first); round r holds rows
+// 32r .. 32r+31, one per lane, and every lane of the round runs the same number of float4 weight groups G_r
+// (rows padded with zero weights), so the inner loop has a warp-uniform trip count.  The kernel reads the
+// magnitude tile with 128-bit loads, so a row's read window must start on a 16-byte boundary (`align` tile
+// elements) — the slack of the padding is used to slide each window so that the 8 lanes of every quarter
+// warp hit 8 different 16-byte bank groups (greedy placement with restarts; residual conflicts only cost
+// replays, never correctness).  Weights are stored [round group][lane] so their 128-bit loads are
+// conflict-free by construction.
 static int upload_filterbank(b200mel_plan *pl, const float *W, int n_mels, int F) {
     struct Row { int m, lo, cnt; };
+    const int align = pl->pair ? 2 : 4;  // tile elements per 16 bytes (float2 pairs vs float)
+    const int tile_len = pl->pair ? kPairTileLen : kSplitTileLen;
     std::vector<Row> rows(n_mels);
     for (int m = 0; m < n_mels; ++m) {
         int first = -1, last = -1;
@@ -161,15 +177,77 @@ static int upload_filterbank(b200mel_plan *pl, const float *W, int n_mels, int F
             }
         rows[m] = {m, first < 0 ? 0 : first, first < 0 ? 0 : last - first + 1};
     }
-    std::stable_sort(rows.begin(), rows.end(), [](const Row &x, const Row &y) { return x.cnt > y.cnt; });
+    auto need = [&](const Row &r) { return (r.cnt + r.lo % align + 3) / 4; };  // groups incl. alignment lead-in
+    std::stable_sort(rows.begin(), rows.end(), [&](const Row &x, const Row &y) { return need(x) > need(y); });
     const int rounds = (n_mels + 31) / 32;
+    if (rounds > kMaxMelRounds) return fail(B200MEL_EUNSUP, "filterbank: more than 256 mel rows");
     std::vector<MelEntry> ent((size_t)rounds * 32, MelEntry{0, 0, 0, -1});
     std::vector<float> w;
-    for (int i = 0; i < n_mels; ++i) {
-        const Row &r = rows[i];
-        const int groups = (r.cnt + 3) / 4;
-        ent[i] = MelEntry{r.lo, groups, (int)w.size(), r.m};
-        for (int k = 0; k < groups * 4; ++k) w.push_back(k < r.cnt ? W[(size_t)r.m * F + r.lo + k] : 0.f);
+    uint32_t rng = 12345u;
+    auto rnd = [&]() { rng = rng * 1664525u + 1013904223u; return rng >> 8; };
+    for (int r = 0; r < rounds; ++r) {
+        const int n = std::min(32, n_mels - r * 32);
+        const Row *rr = &rows[r * 32];
+        int G = 1;
+        for (int i = 0; i < n; ++i) G = std::max(G, need(rr[i]));
+        if (4 * G > tile_len) return fail(B200MEL_EUNSUP, "filterbank: row longer than the magnitude tile");
+        pl->round_groups[r] = G;
+        pl->round_wbase[r] = (int)(w.size() / 4);
+        // candidate window starts of every row
+        std::vector<std::vector<int>> opts(n);
+        for (int i = 0; i < n; ++i) {
+            const int lo_min = std::max(0, rr[i].lo + rr[i].cnt - 4 * G), lo_max = std::min(rr[i].lo, tile_len - 4 * G);
+            for (int l = (lo_min + align - 1) / align * align; l <= lo_max; l += align) opts[i].push_back(l);
+            if (opts[i].empty()) opts[i].push_back(std::max(0, lo_max / align * align));  // cannot happen (G covers it)
+        }
+        int best_cost = 1 << 30;
+        std::vector<int> best_lane(n), best_lo(n);
+        for (int trial = 0; trial < 200 && best_cost > 4; ++trial) {
+            std::vector<int> order(n);
+            for (int i = 0; i < n; ++i) order[i] = i;
+            for (int i = n - 1; i > 0; --i) std::swap(order[i], order[rnd() % (i + 1)]);
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return opts[x].size() < opts[y].size(); });
+            int used[4][8] = {{0}}, qsize[4] = {0};
+            std::vector<int> lane(n), lo(n);
+            for (int oi = 0; oi < n; ++oi) {
+                const int i = order[oi];
+                int bq = -1, bl = 0, bkey = 1 << 30;
+                const int q0 = rnd() % 4;
+                for (int dq = 0; dq < 4; ++dq) {
+                    const int q = (q0 + dq) % 4;
+                    if (qsize[q] >= 8) continue;
+                    for (int l : opts[i]) {
+                        const int key = used[q][(l / align) % 8] * 16 + qsize[q];
+                        if (key < bkey) bkey = key, bq = q, bl = l;
+                    }
+                }
+                used[bq][(bl / align) % 8]++;
+                lane[i] = bq * 8 + qsize[bq]++;
+                lo[i] = bl;
+            }
+            int cost = 0;
+            for (int q = 0; q < 4; ++q) {
+                int mx = 0;
+                for (int k = 0; k < 8; ++k) mx = std::max(mx, used[q][k]);
+                cost += mx;
+            }
+            if (cost < best_cost) best_cost = cost, best_lane = lane, best_lo = lo;
+        }
+        // weights of the round: [g][lane] float4
+        const size_t base = w.size();
+        w.resize(base + (size_t)G * 32 * 4, 0.f);
+        for (int i = 0; i < n; ++i) {
+            const Row &row = rr[i];
+            MelEntry &e = ent[(size_t)r * 32 + best_lane[i]];
+            e.lo = best_lo[i];
+            e.groups = need(row);
+            e.m = row.m;
+            for (int k = 0; k < 4 * G; ++k) {
+                const int bin = e.lo + k;
+                if (bin >= row.lo && bin < row.lo + row.cnt)
+                    w[base + ((size_t)(k / 4) * 32 + best_lane[i]) * 4 + k % 4] = W[(size_t)row.m * F + bin];
+            }
+        }
     }
     if (w.empty()) w.resize(4, 0.f);
     free_mel_tables(pl);
@@ -185,15 +263,26 @@ static int upload_filterbank(b200mel_plan *pl, const float *W, int n_mels, int F
 }
 
 typedef void (*kernel_fn)(const KParams);
-static kernel_fn pick_kernel(bool pair, int spec, bool mel, int power) {
+// The mel kernels exist in 16 / 20 / 24-warp builds (128 / 96 / 80 registers per thread); the spectrum-output
+// kernels are store-bound and only built for 16 warps.
+template <int kWarps>
+static kernel_fn pick_mel_kernel(bool pair, int power) {
+    if (pair) return power == 2 ? logmel_kernel<true, 0, true, 2, kWarps> : logmel_kernel<true, 0, true, 1, kWarps>;
+    return power == 2 ? logmel_kernel<false, 0, true, 2, kWarps> : logmel_kernel<false, 0, true, 1, kWarps>;
+}
+static kernel_fn pick_kernel(bool pair, int spec, bool mel, int power, int warps) {
     if (mel) {
-        if (pair) return power == 2 ? logmel_kernel<true, 0, true, 2> : logmel_kernel<true, 0, true, 1>;
-        return power == 2 ? logmel_kernel<false, 0, true, 2> : logmel_kernel<false, 0, true, 1>;
+        if (warps > 20) return pick_mel_kernel<24>(pair, power);
+        if (warps > 16) return pick_mel_kernel<20>(pair, power);
+        return pick_mel_kernel<16>(pair, power);
     }
     switch (spec) {
-        case B200MEL_SPEC_MAG_PHASE: return pair ? logmel_kernel<true, 1, false, 1> : logmel_kernel<false, 1, false, 1>;
-        case B200MEL_SPEC_RE_IM: return pair ? logmel_kernel<true, 2, false, 1> : logmel_kernel<false, 2, false, 1>;
-        default: return pair ? logmel_kernel<true, 3, false, 1> : logmel_kernel<false, 3, false, 1>;
+        case B200MEL_SPEC_MAG_PHASE:
+            return pair ? logmel_kernel<true, 1, false, 1, 16> : logmel_kernel<false, 1, false, 1, 16>;
+        case B200MEL_SPEC_RE_IM:
+            return pair ? logmel_kernel<true, 2, false, 1, 16> : logmel_kernel<false, 2, false, 1, 16>;
+        default:
+            return pair ? logmel_kernel<true, 3, false, 1, 16> : logmel_kernel<false, 3, false, 1, 16>;
     }
 }
 
@@ -307,8 +396,9 @@ int b200mel_plan_create(const b200mel_config *cfg, b200mel_plan **out) {
         for (int spec = 0; spec <= 3 && e == cudaSuccess; ++spec)
             for (int power = 1; power <= 2 && e == cudaSuccess; ++power) {
                 if (spec != 0 && power == 2) continue;
-                e = cudaFuncSetAttribute(pick_kernel(pl->pair, spec, spec == 0, power),
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+                for (int warps = 16; warps <= (spec == 0 ? 24 : 16) && e == cudaSuccess; warps += 4)
+                    e = cudaFuncSetAttribute(pick_kernel(pl->pair, spec, spec == 0, power, warps),
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
             }
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute (is the library built for this GPU?)"); break; }
     } while (0);
@@ -395,6 +485,7 @@ int b200mel_forward(const b200mel_plan *pl, const float *wav, int64_t B, int64_t
     p.n_freq = pl->n_freq;
     p.mel_rounds = pl->mel_rounds;
     p.mel_w_len = pl->mel_w_len;
+    for (int r = 0; r < kMaxMelRounds; ++r) p.round_groups[r] = pl->round_groups[r], p.round_wbase[r] = pl->round_wbase[r];
     p.off_window = pl->off_window;
     p.off_entries = pl->off_entries;
     p.off_melw = pl->off_melw;
@@ -406,29 +497,47 @@ int b200mel_forward(const b200mel_plan *pl, const float *wav, int64_t B, int64_t
     p.out_a = out_a;
     p.out_b = out_b;
     p.mag_eps = pl->cfg.mag_eps;
+    p.lo = -INFINITY;
+    p.hi = INFINITY;
+    p.norm_scale = 1.f;
+    p.norm_bias = 0.f;
+    p.ep_floor = -INFINITY;
     if (epi) {
-        p.log_kind = epi->log_kind;
-        p.log_arg = epi->log_arg;
-        p.has_lo = epi->has_clamp_lo;
-        p.lo = epi->clamp_lo;
-        p.has_hi = epi->has_clamp_hi;
-        p.hi = epi->clamp_hi;
-        p.norm = epi->norm_mel;
-        if (p.norm) p.norm_scale = 2.0f / (p.hi - p.lo);
+        p.use_log = epi->log_kind != B200MEL_LOG_NONE;
+        if (epi->log_kind == B200MEL_LOG_LN_OFFSET) p.ep_offset = epi->log_arg;
+        else if (p.use_log) p.ep_floor = epi->log_arg;
+        p.log_scale = epi->log_kind == B200MEL_LOG_LOG10_FLOOR ? 0.301029995663981195f : 0.693147180559945309f;
+        if (epi->has_clamp_lo) p.lo = epi->clamp_lo;
+        if (epi->has_clamp_hi) p.hi = epi->clamp_hi;
+        if (epi->norm_mel) {  // (y - lo) / (hi - lo) * 2 - 1
+            p.norm_scale = 2.0f / (p.hi - p.lo);
+            p.norm_bias = -p.lo * p.norm_scale - 1.0f;
+        }
     }
-    p.tasks_per_clip = (T + pl->pair_frames - 1) / pl->pair_frames;
-    p.n_tasks = p.tasks_per_clip * B;
+    const long long tpc = (T + pl->pair_frames - 1) / pl->pair_frames;
+    p.tasks_per_clip = (int)tpc;
+    p.n_tasks = tpc * B;
     long long n_cta = (p.n_tasks + pl->n_warps - 1) / pl->n_warps;
     if (n_cta > pl->num_sms) n_cta = pl->num_sms;  // persistent: one CTA per SM, warps stride over the tasks
+    const long long stride = n_cta * pl->n_warps;
+    p.stride_b = (int)(stride / tpc);
+    p.stride_q = (int)(stride % tpc);
 
     cudaStream_t st = (cudaStream_t)stream;
     // mel and spectrum outputs come from separately specialised kernels (no reference module needs both at once)
     if (out_mel) {
-        pick_kernel(pl->pair, 0, true, pl->cfg.power)<<<(unsigned)n_cta, pl->n_warps * 32, pl->smem_bytes, st>>>(p);
+        pick_kernel(pl->pair, 0, true, pl->cfg.power, pl->n_warps)<<<(unsigned)n_cta, pl->n_warps * 32, pl->smem_bytes, st>>>(p);
         g_launches.fetch_add(1);
     }
     if (spec_kind) {
-        pick_kernel(pl->pair, spec_kind, false, 1)<<<(unsigned)n_cta, pl->n_warps * 32, pl->smem_bytes, st>>>(p);
+        // spectrum kernels are built for <= 16 warps: re-derive the launch shape for them
+        const int sw = pl->n_warps > 16 ? 16 : pl->n_warps;
+        long long s_cta = (p.n_tasks + sw - 1) / sw;
+        if (s_cta > pl->num_sms) s_cta = pl->num_sms;
+        const long long s_stride = s_cta * sw;
+        p.stride_b = (int)(s_stride / tpc);
+        p.stride_q = (int)(s_stride % tpc);
+        pick_kernel(pl->pair, spec_kind, false, 1, sw)<<<(unsigned)s_cta, sw * 32, pl->smem_bytes, st>>>(p);
         g_launches.fetch_add(1);
     }
     cudaError_t e = cudaGetLastError();

@@ -25,7 +25,7 @@
 
 namespace b200mel {
 
-constexpr int kMaxWarps = 16;
+constexpr int kMaxWarps = 24;  // upper bound over all kernel variants (mbarrier array size)
 constexpr int kBufStride = 33;                           // float2 per transposed row (+1 pad)
 constexpr int kXposeBytes = 32 * kBufStride * 8;          // 8448
 constexpr int kTileBytes = 4160;                          // magnitude tile
@@ -33,10 +33,12 @@ constexpr int kStageOff = 4224;                           // stage offset inside
 constexpr int kPairTileLen = 520;                         // float2 entries (513 used, tail zeroed)
 constexpr int kSplitTileLen = 1032;                       // float entries (1025 used, tail zeroed)
 
+constexpr int kMaxMelRounds = 8;  // 32 rows per round -> up to 256 mel rows
+
 struct MelEntry {  // one filterbank row as seen by one lane in one round
-    int lo;        // first spectrum bin
-    int groups;    // number of float4 weight groups (row length padded to a multiple of 4 with zeros)
-    int woff;      // float offset of the row's weights in the shared weight array (multiple of 4)
+    int lo;        // first spectrum bin of the row's read window (16-byte aligned in the tile, slid for bank spread)
+    int groups;    // float4 weight groups the row itself needs (informational; the loop runs the round's count)
+    int woff;      // unused (weights are addressed [round base + group][lane])
     int m;         // mel row index, -1 = idle lane
 };
 
@@ -55,16 +57,19 @@ struct KParams {
     const MelEntry *mel_entries;  // [rounds][32]
     const float *mel_w;           // [mel_w_len]
     int n_mels, n_freq, mel_rounds, mel_w_len;
+    int round_groups[kMaxMelRounds];  // float4 groups every lane runs in round r (rows padded with zero weights)
+    int round_wbase[kMaxMelRounds];   // float4 index of the round's weights, stored [group][lane]
     // shared memory layout (bytes from the dynamic smem base)
     int off_window, off_entries, off_melw, off_bar, off_regions, region_bytes, stage_bytes;
     // outputs
     float *out_mel, *out_a, *out_b;
     float mag_eps;
-    int log_kind;
-    float log_arg;
-    int has_lo, has_hi, norm;
-    float lo, hi, norm_scale;
-    long long tasks_per_clip, n_tasks;
+    // branch-free epilogue: y = min(max(lg2(max(x, floor) + offset) * log_scale, lo), hi) * norm_scale + norm_bias
+    int use_log;
+    float ep_floor, ep_offset, log_scale, lo, hi, norm_scale, norm_bias;
+    // task list: task = b * tasks_per_clip + q; the grid-wide warp stride is pre-split as stride_b * tasks_per_clip + stride_q
+    long long n_tasks;
+    int tasks_per_clip, stride_b, stride_q;
 };
 
 // ------------------------------------------------------------------------------------------- PTX helpers
@@ -101,18 +106,6 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     return y;
 }
 
-// ln / log10 through one MUFU.LG2 (abs. error ~1e-6 on the log value, two orders below the 1e-4 tolerance)
-__device__ __forceinline__ float fast_ln(float x) {
-    float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y * 0.693147180559945309f;
-}
-__device__ __forceinline__ float fast_log10(float x) {
-    float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y * 0.301029995663981195f;
-}
-
 __device__ __forceinline__ int frames_of(int Li, int n_fft, int hop, int pad) {
     int span = Li + 2 * pad - n_fft;
     return span < 0 ? 0 : span / hop + 1;
@@ -123,18 +116,17 @@ __device__ __forceinline__ int reflect_index(int i, int Li) {
     return min(max(i, 0), Li - 1);
 }
 
+// ln / log10 through one MUFU.LG2 (abs. error ~1e-6 on the log value, two orders below the 1e-4 tolerance);
+// clamps are +-inf and the affine is the identity when the caller did not ask for them.
 __device__ __forceinline__ float epilogue(float x, const KParams &p) {
     float y = x;
-    if (p.log_kind == B200MEL_LOG_LN_OFFSET)
-        y = fast_ln(x + p.log_arg);
-    else if (p.log_kind == B200MEL_LOG_LN_FLOOR)
-        y = fast_ln(fmaxf(x, p.log_arg));
-    else if (p.log_kind == B200MEL_LOG_LOG10_FLOOR)
-        y = fast_log10(fmaxf(x, p.log_arg));
-    if (p.has_lo) y = fmaxf(y, p.lo);
-    if (p.has_hi) y = fminf(y, p.hi);
-    if (p.norm) y = (y - p.lo) * p.norm_scale - 1.0f;
-    return y;
+    if (p.use_log) {  // warp-uniform
+        float t = fmaxf(x, p.ep_floor) + p.ep_offset;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t));
+        y *= p.log_scale;
+    }
+    y = fminf(fmaxf(y, p.lo), p.hi);
+    return fmaf(y, p.norm_scale, p.norm_bias);
 }
 
 template <int kPower>
@@ -153,11 +145,10 @@ struct Task {
 };
 
 template <bool kPair>
-__device__ __forceinline__ Task decode_task(const KParams &p, long long task) {
+__device__ __forceinline__ Task decode_task(const KParams &p, long long b, int q) {
     Task t;
-    t.b = task / p.tasks_per_clip;
-    const int q = (int)(task - t.b * p.tasks_per_clip);
-    t.Li = p.lengths ? min(__ldg(p.lengths + t.b), p.L) : p.L;
+    t.b = b;
+    t.Li = p.lengths ? min(__ldg(p.lengths + b), p.L) : p.L;
     const int Ti = p.lengths ? min(frames_of(t.Li, p.n_fft, p.hop, p.pad), p.T) : p.T;
     t.t0 = q * p.pair_frames;
     t.valid0 = t.t0 < Ti;
@@ -193,8 +184,9 @@ __device__ __forceinline__ void issue_stage(const KParams &p, const Task &t, flo
 }
 
 // kSpec: B200MEL_SPEC_* ; kMel: apply the filterbank + epilogue ; kPower: 1 magnitude, 2 power
-template <bool kPair, int kSpec, bool kMel, int kPower>
-__global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams p) {
+// kWarps: warps per CTA the variant is compiled for (register budget = 65536 / (32 kWarps))
+template <bool kPair, int kSpec, bool kMel, int kPower, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_warps = blockDim.x >> 5;
@@ -205,6 +197,30 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
     const MelEntry *s_ent = reinterpret_cast<const MelEntry *>(smem_raw + p.off_entries);
     const float *s_melw = reinterpret_cast<const float *>(smem_raw + p.off_melw);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + p.off_bar);
+    unsigned char *region = smem_raw + p.off_regions + warp * p.region_bytes;
+    float2 *buf = reinterpret_cast<float2 *>(region);          // transpose buffer
+    float2 *tile2 = reinterpret_cast<float2 *>(region);        // pair-mode magnitude tile
+    float *tile1 = reinterpret_cast<float *>(region);          // split-mode magnitude tile
+    float *stage = reinterpret_cast<float *>(region + kStageOff);
+    const uint32_t bar = smem_u32(s_bar + warp);
+    uint32_t parity = 0;
+
+    // task = cb * tasks_per_clip + cq, advanced by the grid-wide warp stride without any division
+    const long long stride = (long long)gridDim.x * n_warps;
+    long long task = (long long)blockIdx.x * n_warps + warp;
+    long long cb = task / p.tasks_per_clip;
+    int cq = (int)(task - cb * p.tasks_per_clip);
+
+    // every warp owns its mbarrier: arm it and get the first task's samples moving before the tables are loaded
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (task < p.n_tasks) {
+            const Task t = decode_task<kPair>(p, cb, cq);
+            if (t.valid0) issue_stage<kPair>(p, t, stage, bar);
+        }
+    }
+    __syncwarp();
     {
         const int4 *g;
         int4 *s;
@@ -222,32 +238,18 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
             s = reinterpret_cast<int4 *>(smem_raw + p.off_melw);
             for (int i = threadIdx.x; i < p.mel_w_len / 4; i += blockDim.x) s[i] = __ldg(g + i);
         }
-        if (threadIdx.x < n_warps) mbar_init(smem_u32(s_bar + threadIdx.x), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();  // the only block-wide barrier; warps are independent from here on
-
-    unsigned char *region = smem_raw + p.off_regions + warp * p.region_bytes;
-    float2 *buf = reinterpret_cast<float2 *>(region);          // transpose buffer
-    float2 *tile2 = reinterpret_cast<float2 *>(region);        // pair-mode magnitude tile
-    float *tile1 = reinterpret_cast<float *>(region);          // split-mode magnitude tile
-    float *stage = reinterpret_cast<float *>(region + kStageOff);
-    const uint32_t bar = smem_u32(s_bar + warp);
-    uint32_t parity = 0;
-
-    const long long stride = (long long)gridDim.x * n_warps;
-    long long task = (long long)blockIdx.x * n_warps + warp;
 
     float2 wl = make_float2(1.f, 0.f);
     if (!kPair) wl = __ldg(p.tw_post + lane);
 
-    if (task < p.n_tasks && lane == 0) {
-        const Task t = decode_task<kPair>(p, task);
-        if (t.valid0) issue_stage<kPair>(p, t, stage, bar);
-    }
-
     for (; task < p.n_tasks; task += stride) {
-        const Task t = decode_task<kPair>(p, task);
+        const Task t = decode_task<kPair>(p, cb, cq);
+        // next task of this warp
+        cb += p.stride_b;
+        cq += p.stride_q;
+        if (cq >= p.tasks_per_clip) cq -= p.tasks_per_clip, ++cb;
         const long long b = t.b;
         const int t0 = t.t0;
         float2 a[32];
@@ -298,13 +300,27 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
             __syncwarp();  // every lane has consumed the stage before the transpose buffer overwrites it
             static_for<0, 32>([&](auto k1_) {
                 constexpr int k1 = decltype(k1_)::value;
-                float2 v = a[fft32_pos(k1)];
-                if constexpr (k1 > 0) v = cmul(v, s_tw[k1 * 32 + lane]);
-                buf[k1 * kBufStride + lane] = v;
+                buf[k1 * kBufStride + lane] = a[fft32_pos(k1)];
             });
             __syncwarp();
+            // read back transposed (lane = k1, slot = n2) and apply the inter-pass twiddle W_1024^{n2 k1} on the
+            // read side: the a[] registers are free here, so each half issues its 16 + 16 loads back to back
+            // (deep memory-level parallelism) instead of serialising load -> multiply -> store per element.
+            {
+                float2 tw[16];
 #pragma unroll
-            for (int n2 = 0; n2 < 32; ++n2) a[n2] = buf[lane * kBufStride + n2];
+                for (int n2 = 0; n2 < 16; ++n2) a[n2] = buf[lane * kBufStride + n2];
+#pragma unroll
+                for (int n2 = 1; n2 < 16; ++n2) tw[n2] = s_tw[n2 * 32 + lane];
+#pragma unroll
+                for (int n2 = 1; n2 < 16; ++n2) a[n2] = cmul(a[n2], tw[n2]);
+#pragma unroll
+                for (int n2 = 16; n2 < 32; ++n2) a[n2] = buf[lane * kBufStride + n2];
+#pragma unroll
+                for (int n2 = 0; n2 < 16; ++n2) tw[n2] = s_tw[(n2 + 16) * 32 + lane];
+#pragma unroll
+                for (int n2 = 16; n2 < 32; ++n2) a[n2] = cmul(a[n2], tw[n2 - 16]);
+            }
             __syncwarp();  // transpose buffer is dead: magnitude tile and next stage may reuse it
         }
 
@@ -312,7 +328,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
         {
             const long long nt = task + stride;
             if (nt < p.n_tasks && lane == 0) {
-                const Task n = decode_task<kPair>(p, nt);
+                const Task n = decode_task<kPair>(p, cb, cq);
                 if (n.valid0) issue_stage<kPair>(p, n, stage, bar);
             }
         }
@@ -441,32 +457,42 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
 
         // ---------------------------------------------------------------------- banded mel + log epilogue
         if constexpr (kMel) {
+            float *orow = p.out_mel + b * p.n_mels * (long long)p.T + t0;
+#pragma unroll 1
             for (int r = 0; r < p.mel_rounds; ++r) {
-                const MelEntry e = s_ent[r * 32 + lane];
-                const float4 *w4 = reinterpret_cast<const float4 *>(s_melw + e.woff);
-                float acc0 = 0.f, acc1 = 0.f;
+                const int4 e4 = reinterpret_cast<const int4 *>(s_ent)[r * 32 + lane];  // one 128-bit load
+                MelEntry e;
+                e.lo = e4.x, e.m = e4.w;
+                const int groups = p.round_groups[r];  // warp-uniform trip count: no divergence inside a round
+                const float4 *w4 = reinterpret_cast<const float4 *>(s_melw) + p.round_wbase[r] + lane;
+                float acc0 = 0.f, acc1 = 0.f, b0 = 0.f, b1 = 0.f;  // two independent FFMA chains per frame
                 if constexpr (kPair) {
-                    const float2 *mg = tile2 + e.lo;
-                    for (int g = 0; g < e.groups; ++g) {
-                        const float4 w = w4[g];
-                        const float2 v0 = mg[4 * g], v1 = mg[4 * g + 1], v2 = mg[4 * g + 2], v3 = mg[4 * g + 3];
-                        acc0 = fmaf(w.x, v0.x, acc0), acc1 = fmaf(w.x, v0.y, acc1);
-                        acc0 = fmaf(w.y, v1.x, acc0), acc1 = fmaf(w.y, v1.y, acc1);
-                        acc0 = fmaf(w.z, v2.x, acc0), acc1 = fmaf(w.z, v2.y, acc1);
-                        acc0 = fmaf(w.w, v3.x, acc0), acc1 = fmaf(w.w, v3.y, acc1);
+                    // tile2[k] = {|X_t[k]|, |X_t+1[k]|}: one 128-bit load brings two bins of both frames
+                    const float4 *mg = reinterpret_cast<const float4 *>(tile2 + e.lo);
+#pragma unroll 2
+                    for (int g = 0; g < groups; ++g) {
+                        const float4 w = w4[g * 32];
+                        const float4 u = mg[2 * g], v = mg[2 * g + 1];
+                        acc0 = fmaf(w.x, u.x, acc0), acc1 = fmaf(w.x, u.y, acc1);
+                        b0 = fmaf(w.y, u.z, b0), b1 = fmaf(w.y, u.w, b1);
+                        acc0 = fmaf(w.z, v.x, acc0), acc1 = fmaf(w.z, v.y, acc1);
+                        b0 = fmaf(w.w, v.z, b0), b1 = fmaf(w.w, v.w, b1);
                     }
                 } else {
-                    const float *mg = tile1 + e.lo;
-                    for (int g = 0; g < e.groups; ++g) {
-                        const float4 w = w4[g];
-                        acc0 = fmaf(w.x, mg[4 * g], acc0);
-                        acc0 = fmaf(w.y, mg[4 * g + 1], acc0);
-                        acc0 = fmaf(w.z, mg[4 * g + 2], acc0);
-                        acc0 = fmaf(w.w, mg[4 * g + 3], acc0);
+                    const float4 *mg = reinterpret_cast<const float4 *>(tile1 + e.lo);
+#pragma unroll 2
+                    for (int g = 0; g < groups; ++g) {
+                        const float4 w = w4[g * 32];
+                        const float4 u = mg[g];
+                        acc0 = fmaf(w.x, u.x, acc0);
+                        b0 = fmaf(w.y, u.y, b0);
+                        acc0 = fmaf(w.z, u.z, acc0);
+                        b0 = fmaf(w.w, u.w, b0);
                     }
                 }
+                acc0 += b0, acc1 += b1;
                 if (e.m >= 0) {
-                    float *o = p.out_mel + (b * p.n_mels + e.m) * (long long)p.T + t0;
+                    float *o = orow + (long long)e.m * p.T;
                     o[0] = epilogue(acc0, p);
                     if (kPair && t.valid1) o[1] = epilogue(acc1, p);
                 }
