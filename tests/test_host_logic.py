@@ -1,0 +1,195 @@
+"""Host-side logic that needs no GPU: reference-shaped constructors / buffers / state_dicts, calculate helpers,
+settings, the post-collate feature hook, clip sharding and the world_size-2 gather over gloo."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mel_oracle as mo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_modules_mirror_reference_signatures_and_buffers(built_lib, golden):
+    import inspect
+
+    from pytorch_sound_b200.interface.hifi_gan import AudioParameters, MelSpectrogram
+    from pytorch_sound_b200.models import transforms as T
+
+    def params(cls):
+        return [(n, p.default) for n, p in inspect.signature(cls.__init__).parameters.items() if n != "self"]
+
+    E = inspect.Parameter.empty
+    # models/transforms.py:211-213
+    assert params(T.LogMelSpectrogram) == [("sample_rate", E), ("mel_size", E), ("n_fft", E), ("win_length", E),
+                                           ("hop_length", E), ("min_db", None), ("max_db", None), ("mel_min", 0.),
+                                           ("mel_max", None)]
+    assert params(T.STFT) == [("filter_length", 1024), ("hop_length", 512), ("win_length", None), ("window", "hann")]
+    assert params(T.STFTTorchAudio) == [("filter_length", 1024), ("hop_length", 512), ("win_length", None),
+                                        ("n_fft", None), ("window", "hann")]
+    assert params(T.Audio2Mel) == [("n_fft", 1024), ("hop_length", 256), ("win_length", 1024),
+                                   ("sampling_rate", 22050), ("n_mel_channels", 80), ("mel_fmin", 0.0),
+                                   ("mel_fmax", None)]
+    assert params(MelSpectrogram) == [("sampling_rate", 22050), ("n_fft", 1024), ("window_size", 1024),
+                                      ("hop_size", 256), ("num_mels", 80), ("fmin", 0.), ("fmax", 8000.)]
+    fwd = inspect.signature(T.LogMelSpectrogram.forward).parameters
+    assert list(fwd)[:3] == ["self", "wav", "log_offset"] and fwd["log_offset"].default == 1e-6
+    assert inspect.signature(MelSpectrogram.forward).parameters["is_center"].default is False
+    assert vars(AudioParameters()) == {} and AudioParameters.fmax == 8000.
+
+    lm = T.LogMelSpectrogram(22050, 80, 1024, 1024, 256, -50, 30, 0., 8000.)
+    assert lm.min_db == pytest.approx(np.log(1e-5)) and lm.max_db == pytest.approx(np.log(1e3))
+    assert np.array_equal(lm.mel_filter.numpy(), golden["buf.mel_filter"])  # the reference module's own buffer
+    assert set(lm.state_dict()) == {"mel_filter", "stft.square_window"}
+    np.testing.assert_allclose(lm.stft.square_window.numpy(), golden["buf.stft_window_sq"], atol=2e-7)
+    assert T.LogMelSpectrogram(22050, 80, 1024, 1024, 256, 0, 0).min_db is None  # `if min_db:` truthiness (:222)
+    hf = MelSpectrogram()
+    assert set(hf.state_dict()) == {"mel_filter", "window"} and hf.pad_size == 384
+    np.testing.assert_allclose(hf.window.numpy(), golden["buf.hifi_window"], atol=2e-7)
+    a2m = T.Audio2Mel()
+    assert set(a2m.state_dict()) == {"mel_basis", "window"} and a2m.mel_basis.shape == (80, 513)
+    with pytest.raises(ValueError):
+        T.LogMelSpectrogram(22050, 80, 2048, 1024, 256)  # reference shapes mismatch too
+    with pytest.raises(AssertionError):
+        T.STFT(filter_length=512, win_length=1024)  # models/transforms.py:28
+    with pytest.raises(NotImplementedError):
+        T.STFTTorchAudio(window="hamming")
+
+
+def test_state_dict_roundtrip_with_reference_keys(built_lib):
+    from pytorch_sound_b200.models import transforms as T
+
+    lm = T.LogMelSpectrogram(22050, 80, 1024, 1024, 256)
+    sd = {k: v.clone() for k, v in lm.state_dict().items()}
+    sd["stft.forward_basis"] = torch.zeros(1026, 1, 1024)  # present in reference checkpoints
+    sd["stft.inverse_basis"] = torch.zeros(1026, 1, 1024)
+    lm.load_state_dict(sd)  # strict load must accept the reference's extra conv kernels
+    assert not lm._fb_dirty
+    sd["mel_filter"] = sd["mel_filter"] * 2
+    lm.load_state_dict(sd)
+    assert lm._fb_dirty  # a different filterbank switches the module to a private plan
+
+
+def test_cpu_tensors_raise_not_fallback(built_lib):
+    from pytorch_sound_b200.interface.hifi_gan import MelSpectrogram
+    from pytorch_sound_b200.models import transforms as T
+
+    x = torch.zeros(2, 4096)
+    for call in (lambda: T.LogMelSpectrogram(22050, 80, 1024, 1024, 256)(x), lambda: T.STFT().transform(x),
+                 lambda: T.STFTTorchAudio().transform(x), lambda: T.Audio2Mel()(x.unsqueeze(1)),
+                 lambda: MelSpectrogram()(x), lambda: MelSpectrogram()(x, is_center=True)):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
+
+
+def test_calculate_and_settings(golden):
+    from pytorch_sound_b200 import settings
+    from pytorch_sound_b200.utils.calculate import db2log, norm_mel, unnorm_mel
+
+    assert db2log(np.array(-50.)) == pytest.approx(np.log(1e-5)) and db2log(30) == pytest.approx(np.log(1e3))
+    assert float(db2log(torch.tensor(-50.))) == pytest.approx(np.log(1e-5), rel=1e-6)
+    np.testing.assert_allclose(golden["kat.db2log"], [db2log(-50), db2log(30)], rtol=1e-12)
+    xs = torch.linspace(-1, 1, 11)
+    np.testing.assert_allclose(unnorm_mel(xs).numpy(), golden["kat.unnorm_mel"], atol=5e-6)
+    np.testing.assert_allclose(norm_mel(unnorm_mel(xs)).numpy(), xs.numpy(), atol=1e-6)
+    y = torch.from_numpy(golden["clips.logmel_clamped"])
+    np.testing.assert_allclose(norm_mel(y).numpy(), golden["clips.norm_mel"], atol=1e-6)
+    np.testing.assert_allclose(norm_mel(y.numpy()), golden["clips.norm_mel"], atol=1e-6)
+    kw = settings.logmel_kwargs()
+    assert (kw["sample_rate"], kw["n_fft"], kw["hop_length"], kw["mel_size"], kw["mel_max"]) == (22050, 1024, 256, 80, 8000.)
+    assert settings.SPEC_SIZE == 513 and settings.HOP_STRIDE == 4
+
+
+def test_mel_to_mfcc_matches_torchaudio():
+    torchaudio = pytest.importorskip("torchaudio")
+    from pytorch_sound_b200.models.transforms import MelToMFCC
+
+    m = MelToMFCC(40, 80)
+    ref = torchaudio.functional.create_dct(40, 80, "ortho").transpose(0, 1)  # models/transforms.py:427-428
+    np.testing.assert_allclose(m.dct_mat.numpy(), ref.numpy(), atol=1e-6)
+    x = torch.randn(2, 80, 7)
+    np.testing.assert_allclose(m(x).numpy(), torch.matmul(ref, x).numpy(), atol=1e-5)
+
+
+def test_gpu_feature_loader_layout():
+    """pad_collate_fn-shaped batches: [wav (B,L), label (B,), mask (B,L)] -> features inserted before the mask."""
+    from pytorch_sound_b200.data.feature_loader import GpuFeatureLoader
+
+    class FakeMel(torch.nn.Module):
+        def forward(self, wav, lengths=None):
+            out = wav[:, None, ::256].repeat(1, 80, 1)
+            if lengths is not None:
+                out = out + lengths.view(-1, 1, 1).to(out.dtype)
+            return out
+
+    lens = [1024, 700]
+    wav = torch.zeros(2, 1024)
+    mask = torch.zeros(2, 1024)
+    for i, n in enumerate(lens):
+        wav[i, :n] = 1.0
+        mask[i, :n] = 1.0
+    loader = [[wav, torch.tensor([3, 4]), mask]]
+    out = list(GpuFeatureLoader(loader, [(0, FakeMel())], device="cpu", mask_index=-1))[0]
+    assert len(out) == 4 and out[2].shape == (2, 80, 4) and torch.equal(out[3], mask)
+    assert torch.equal(out[2][:, 0, 0], torch.tensor([1025., 701.]))  # lengths derived from the mask
+    out = list(GpuFeatureLoader(loader, [(0, FakeMel())], device="cpu"))[0]
+    assert len(out) == 4 and out[3].shape == (2, 80, 4)  # no mask: appended at the end
+    assert len(GpuFeatureLoader(loader, [], device="cpu")) == 1
+
+
+def test_shard_range():
+    from pytorch_sound_b200.distributed import shard_range
+
+    for n, g in [(2048, 8), (256, 1), (10, 4), (3, 8), (0, 2)]:
+        ranges = [shard_range(n, r, g) for r in range(g)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(g - 1))
+        sizes = [b - a for a, b in ranges]
+        assert max(sizes) - min(sizes) <= 1
+    assert shard_range(2048, 3, 8) == (768, 1024)
+    with pytest.raises(ValueError):
+        shard_range(8, 8, 8)
+
+
+def _gloo_worker(rank, world, port, n_clips, q):
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    from pytorch_sound_b200.distributed import ShardedExtractor, all_gather_mel, shard_range
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        full = torch.arange(n_clips * 3 * 4, dtype=torch.float32).reshape(n_clips, 3, 4)
+        a, b = shard_range(n_clips, rank, world)
+        got = all_gather_mel(full[a:b].clone(), n_clips)
+        ok = torch.equal(got, full)
+        # the sharded wrapper: every rank extracts its shard with a stand-in module, then gathers
+        wav = torch.arange(n_clips * 8, dtype=torch.float32).reshape(n_clips, 8)
+        ext = ShardedExtractor(lambda w: w[:, None, ::2] * 2.0)
+        ok = ok and torch.equal(ext(wav), wav[:, None, ::2] * 2.0)
+        ok = ok and ext(wav, gather=False).shape[0] == b - a
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_clips", [8, 7])
+def test_all_gather_mel_world_size_2_gloo(n_clips):
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n_clips, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert results == [(0, True), (1, True)]
