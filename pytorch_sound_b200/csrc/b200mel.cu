@@ -32,6 +32,7 @@ namespace b200mel {
 // ----------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
+static long long *g_dbg = nullptr;  // device buffer for -DB200MEL_PHASE_TIMING builds (b200mel_debug_set_buffer)
 
 static int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -291,6 +292,8 @@ extern "C" {
 int b200mel_version(void) { return B200MEL_VERSION; }
 const char *b200mel_last_error(void) { return g_err.c_str(); }
 int64_t b200mel_launch_count(void) { return g_launches.load(); }
+// debug hook, not part of include/b200mel.h: device pointer to >= 16 int64 accumulators (phase-timing builds)
+void b200mel_debug_set_buffer(long long *dev_ptr) { g_dbg = dev_ptr; }
 
 int b200mel_mel_filterbank(int32_t sr, int32_t n_fft, int32_t n_mels, double fmin, double fmax, int32_t mel_scale,
                            int32_t mel_norm, float *out) {
@@ -497,6 +500,7 @@ int b200mel_forward(const b200mel_plan *pl, const float *wav, int64_t B, int64_t
     p.out_a = out_a;
     p.out_b = out_b;
     p.mag_eps = pl->cfg.mag_eps;
+    p.dbg = g_dbg;
     p.lo = -INFINITY;
     p.hi = INFINITY;
     p.norm_scale = 1.f;

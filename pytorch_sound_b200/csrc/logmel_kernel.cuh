@@ -23,6 +23,22 @@
 #include "../../include/b200mel.h"
 #include "fft32.cuh"
 
+// Optional phase timing (tools/phase_timing.py): compile with -DB200MEL_PHASE_TIMING; every warp accumulates the
+// clock64() deltas of its phases into dbg[phase] (one atomicAdd per phase per task).
+#ifdef B200MEL_PHASE_TIMING
+// light-weight: one 32-bit clock read per mark, per-thread register accumulators, flushed once at kernel end
+#define PHASE_MARK(i)                                  \
+    do {                                               \
+        const unsigned now_ = (unsigned)clock();       \
+        phase_acc_[i] += now_ - tmark_;                \
+        tmark_ = now_;                                 \
+    } while (0)
+#else
+#define PHASE_MARK(i) \
+    do {              \
+    } while (0)
+#endif
+
 namespace b200mel {
 
 constexpr int kMaxWarps = 24;  // upper bound over all kernel variants (mbarrier array size)
@@ -63,6 +79,7 @@ struct KParams {
     int off_window, off_entries, off_melw, off_bar, off_regions, region_bytes, stage_bytes;
     // outputs
     float *out_mel, *out_a, *out_b;
+    long long *dbg;  // phase-timing accumulators (debug builds only)
     float mag_eps;
     // branch-free epilogue: y = min(max(lg2(max(x, floor) + offset) * log_scale, lo), hi) * norm_scale + norm_bias
     int use_log;
@@ -183,6 +200,67 @@ __device__ __forceinline__ void issue_stage(const KParams &p, const Task &t, flo
     tma_load_1d(smem_u32(dst), reinterpret_cast<const void *>(a16), bytes, bar);
 }
 
+// One mel round for one lane, G float4 weight groups, straight-line: all 3G 128-bit loads are issued before the
+// 8G FFMAs (four independent accumulation chains), so the shared-memory latency is paid once per round instead of
+// once per group.  `w4` points at the lane's first weight group ([group][lane] layout, stride 32 float4).
+template <bool kPair, int G>
+__device__ __forceinline__ void mel_round(const float4 *w4, const void *tile_at_lo, float &acc0, float &acc1) {
+    float b0 = 0.f, b1 = 0.f;
+    if constexpr (kPair) {
+        const float4 *mg = reinterpret_cast<const float4 *>(tile_at_lo);  // {|X_t[k]|, |X_t+1[k]|, |X_t[k+1]|, |X_t+1[k+1]|}
+        float4 w[G], u[G], v[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) w[g] = w4[g * 32], u[g] = mg[2 * g], v[g] = mg[2 * g + 1];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            acc0 = fmaf(w[g].x, u[g].x, acc0), acc1 = fmaf(w[g].x, u[g].y, acc1);
+            b0 = fmaf(w[g].y, u[g].z, b0), b1 = fmaf(w[g].y, u[g].w, b1);
+            acc0 = fmaf(w[g].z, v[g].x, acc0), acc1 = fmaf(w[g].z, v[g].y, acc1);
+            b0 = fmaf(w[g].w, v[g].z, b0), b1 = fmaf(w[g].w, v[g].w, b1);
+        }
+    } else {
+        const float4 *mg = reinterpret_cast<const float4 *>(tile_at_lo);
+        float4 w[G], u[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) w[g] = w4[g * 32], u[g] = mg[g];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            acc0 = fmaf(w[g].x, u[g].x, acc0);
+            b0 = fmaf(w[g].y, u[g].y, b0);
+            acc0 = fmaf(w[g].z, u[g].z, acc0);
+            b0 = fmaf(w[g].w, u[g].w, b0);
+        }
+    }
+    acc0 += b0, acc1 += b1;
+}
+
+// Runs `groups` (warp-uniform) weight groups as straight-line chunks of 8 / 4 / 2 / 1.
+template <bool kPair, int kMaxChunk>
+__device__ __forceinline__ void mel_groups(int groups, const float4 *w4, const unsigned char *tile_at_lo, float &acc0,
+                                           float &acc1) {
+    constexpr int kBytesPerGroup = kPair ? 32 : 16;  // tile bytes one weight group covers
+    if constexpr (kMaxChunk >= 8) {
+        while (groups >= 8) {
+            mel_round<kPair, 8>(w4, tile_at_lo, acc0, acc1);
+            groups -= 8, w4 += 8 * 32, tile_at_lo += 8 * kBytesPerGroup;
+        }
+    } else {
+        while (groups >= 8) {
+            mel_round<kPair, 4>(w4, tile_at_lo, acc0, acc1);
+            groups -= 4, w4 += 4 * 32, tile_at_lo += 4 * kBytesPerGroup;
+        }
+    }
+    if (groups & 4) {
+        mel_round<kPair, 4>(w4, tile_at_lo, acc0, acc1);
+        w4 += 4 * 32, tile_at_lo += 4 * kBytesPerGroup;
+    }
+    if (groups & 2) {
+        mel_round<kPair, 2>(w4, tile_at_lo, acc0, acc1);
+        w4 += 2 * 32, tile_at_lo += 2 * kBytesPerGroup;
+    }
+    if (groups & 1) mel_round<kPair, 1>(w4, tile_at_lo, acc0, acc1);
+}
+
 // kSpec: B200MEL_SPEC_* ; kMel: apply the filterbank + epilogue ; kPower: 1 magnitude, 2 power
 // kWarps: warps per CTA the variant is compiled for (register budget = 65536 / (32 kWarps))
 template <bool kPair, int kSpec, bool kMel, int kPower, int kWarps>
@@ -190,6 +268,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_warps = blockDim.x >> 5;
+#if defined(B200MEL_PHASE_TIMING) || defined(B200MEL_SPAN_TIMING)
+    if (p.dbg && threadIdx.x == 0) {
+        unsigned long long t_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+        atomicMin(reinterpret_cast<unsigned long long *>(p.dbg) + 14, t_);
+    }
+#endif
 
     // ------------------------------------------------------------------ CTA tables -> shared memory
     float2 *s_tw = reinterpret_cast<float2 *>(smem_raw);
@@ -244,6 +329,21 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
     float2 wl = make_float2(1.f, 0.f);
     if (!kPair) wl = __ldg(p.tw_post + lane);
 
+#ifdef B200MEL_PHASE_TIMING
+    unsigned phase_acc_[14];
+#pragma unroll
+    for (int i_ = 0; i_ < 14; ++i_) phase_acc_[i_] = 0;
+    unsigned tmark_ = (unsigned)clock();
+#endif
+    PHASE_MARK(0);  // prologue
+#if defined(B200MEL_PHASE_TIMING) || defined(B200MEL_SPAN_TIMING)
+    if (p.dbg && lane == 0) {
+        unsigned long long t_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+        atomicMin(reinterpret_cast<unsigned long long *>(p.dbg) + 16, t_);   // first warp past the prologue
+        atomicMax(reinterpret_cast<unsigned long long *>(p.dbg) + 17, t_);   // last warp past the prologue
+    }
+#endif
     for (; task < p.n_tasks; task += stride) {
         const Task t = decode_task<kPair>(p, cb, cq);
         // next task of this warp
@@ -257,8 +357,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
         if (t.valid0) {
             const float *row = p.wav + b * p.row_stride;
             const int delta = stage_delta(row, t);
+            PHASE_MARK(1);  // decode
             mbar_wait(bar, parity);
             parity ^= 1;
+            PHASE_MARK(2);  // wait for the TMA stage
             // -------------------------------------------------------------- halo (reflect) fix-up, edge tasks only
             if (t.s_first < 0 || t.s_first + t.span > t.Li) {
                 for (int i = lane; i < t.span; i += 32) {
@@ -270,7 +372,40 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
             // -------------------------------------------------------------- stage -> registers, windowed
             const float *x0 = stage + delta + lane;
             if (kPair) {
-                if (t.valid1) {
+                if (t.valid1 && p.hop == 256) {
+                    // hop = 8 * 32: element j of frame t+1 IS element j+8 of frame t in the stage, so the two frames
+                    // need 40 distinct shared-memory loads per lane instead of 64
+                    if constexpr (kWarps > 16) {  // two halves: 24 loads in flight instead of 40
+                        float raw[24];
+#pragma unroll
+                        for (int j = 0; j < 24; ++j) raw[j] = x0[32 * j];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float w = s_win[32 * j + lane];
+                            a[j].x = raw[j] * w;
+                            a[j].y = raw[j + 8] * w;
+                        }
+                        float raw2[24];
+#pragma unroll
+                        for (int j = 0; j < 24; ++j) raw2[j] = x0[32 * (j + 16)];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float w = s_win[32 * (j + 16) + lane];
+                            a[j + 16].x = raw2[j] * w;
+                            a[j + 16].y = raw2[j + 8] * w;
+                        }
+                    } else {
+                        float raw[40];
+#pragma unroll
+                        for (int j = 0; j < 40; ++j) raw[j] = x0[32 * j];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float w = s_win[32 * j + lane];
+                            a[j].x = raw[j] * w;
+                            a[j].y = raw[j + 8] * w;
+                        }
+                    }
+                } else if (t.valid1) {
                     const float *x1 = x0 + p.hop;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -296,7 +431,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
             }
 
             // -------------------------------------------------------------- 1024-point complex FFT
+            PHASE_MARK(3);  // halo + stage -> registers (windowed)
             fft32(a);  // pass 1: lane = n2, FFT over n1 -> Y[k1] at a[pos(k1)]
+            PHASE_MARK(4);  // pass 1
             __syncwarp();  // every lane has consumed the stage before the transpose buffer overwrites it
             static_for<0, 32>([&](auto k1_) {
                 constexpr int k1 = decltype(k1_)::value;
@@ -307,21 +444,21 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
             // read side: the a[] registers are free here, so each half issues its 16 + 16 loads back to back
             // (deep memory-level parallelism) instead of serialising load -> multiply -> store per element.
             {
-                float2 tw[16];
+                constexpr int kB = kWarps > 16 ? 8 : 16;  // loads in flight per batch (register budget of the variant)
+                static_for<0, 32 / kB>([&](auto h_) {
+                    constexpr int h = decltype(h_)::value;
+                    float2 tw[kB];
 #pragma unroll
-                for (int n2 = 0; n2 < 16; ++n2) a[n2] = buf[lane * kBufStride + n2];
+                    for (int i = 0; i < kB; ++i) a[h * kB + i] = buf[lane * kBufStride + h * kB + i];
 #pragma unroll
-                for (int n2 = 1; n2 < 16; ++n2) tw[n2] = s_tw[n2 * 32 + lane];
+                    for (int i = 0; i < kB; ++i) tw[i] = s_tw[(h * kB + i) * 32 + lane];
 #pragma unroll
-                for (int n2 = 1; n2 < 16; ++n2) a[n2] = cmul(a[n2], tw[n2]);
-#pragma unroll
-                for (int n2 = 16; n2 < 32; ++n2) a[n2] = buf[lane * kBufStride + n2];
-#pragma unroll
-                for (int n2 = 0; n2 < 16; ++n2) tw[n2] = s_tw[(n2 + 16) * 32 + lane];
-#pragma unroll
-                for (int n2 = 16; n2 < 32; ++n2) a[n2] = cmul(a[n2], tw[n2 - 16]);
+                    for (int i = 0; i < kB; ++i)
+                        if (h * kB + i > 0) a[h * kB + i] = cmul(a[h * kB + i], tw[i]);
+                });
             }
             __syncwarp();  // transpose buffer is dead: magnitude tile and next stage may reuse it
+            PHASE_MARK(5);  // transpose + twiddle
         }
 
         // ------------------------------------------------------------------ prefetch the next task's samples
@@ -334,7 +471,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
         }
 
         if (t.valid0) {
+            PHASE_MARK(6);  // prefetch issue
             fft32(a);  // pass 2: lane = k1, FFT over n2 -> Z[k1 + 32 k2] at a[pos(k2)]
+            PHASE_MARK(7);  // pass 2
 
             // -------------------------------------------------------------- real-input separation + magnitudes
             const int partner = (32 - lane) & 31;
@@ -455,51 +594,50 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
             if (!t.valid0) continue;
         }
 
+        PHASE_MARK(8);  // separation + magnitudes
         // ---------------------------------------------------------------------- banded mel + log epilogue
         if constexpr (kMel) {
             float *orow = p.out_mel + b * p.n_mels * (long long)p.T + t0;
+            const int4 *ent4 = reinterpret_cast<const int4 *>(s_ent) + lane;
+            const float4 *wbase = reinterpret_cast<const float4 *>(s_melw) + lane;
+            const unsigned char *tile_bytes = region;
+            int4 e = ent4[0];  // {lo, groups, woff, m}; the next round's entry is fetched while this one computes
 #pragma unroll 1
             for (int r = 0; r < p.mel_rounds; ++r) {
-                const int4 e4 = reinterpret_cast<const int4 *>(s_ent)[r * 32 + lane];  // one 128-bit load
-                MelEntry e;
-                e.lo = e4.x, e.m = e4.w;
-                const int groups = p.round_groups[r];  // warp-uniform trip count: no divergence inside a round
-                const float4 *w4 = reinterpret_cast<const float4 *>(s_melw) + p.round_wbase[r] + lane;
-                float acc0 = 0.f, acc1 = 0.f, b0 = 0.f, b1 = 0.f;  // two independent FFMA chains per frame
-                if constexpr (kPair) {
-                    // tile2[k] = {|X_t[k]|, |X_t+1[k]|}: one 128-bit load brings two bins of both frames
-                    const float4 *mg = reinterpret_cast<const float4 *>(tile2 + e.lo);
-#pragma unroll 2
-                    for (int g = 0; g < groups; ++g) {
-                        const float4 w = w4[g * 32];
-                        const float4 u = mg[2 * g], v = mg[2 * g + 1];
-                        acc0 = fmaf(w.x, u.x, acc0), acc1 = fmaf(w.x, u.y, acc1);
-                        b0 = fmaf(w.y, u.z, b0), b1 = fmaf(w.y, u.w, b1);
-                        acc0 = fmaf(w.z, v.x, acc0), acc1 = fmaf(w.z, v.y, acc1);
-                        b0 = fmaf(w.w, v.z, b0), b1 = fmaf(w.w, v.w, b1);
-                    }
-                } else {
-                    const float4 *mg = reinterpret_cast<const float4 *>(tile1 + e.lo);
-#pragma unroll 2
-                    for (int g = 0; g < groups; ++g) {
-                        const float4 w = w4[g * 32];
-                        const float4 u = mg[g];
-                        acc0 = fmaf(w.x, u.x, acc0);
-                        b0 = fmaf(w.y, u.y, b0);
-                        acc0 = fmaf(w.z, u.z, acc0);
-                        b0 = fmaf(w.w, u.w, b0);
-                    }
+                const int4 cur = e;
+                if (r + 1 < p.mel_rounds) e = ent4[(r + 1) * 32];
+                float acc0 = 0.f, acc1 = 0.f;
+                PHASE_MARK(9);  // round setup
+                mel_groups<kPair, (kWarps > 16 ? 4 : 8)>(p.round_groups[r], wbase + p.round_wbase[r], tile_bytes + cur.x * (kPair ? 8 : 4), acc0,
+                                  acc1);
+                PHASE_MARK(10);  // mel FMAs
+                const float y0 = epilogue(acc0, p), y1 = epilogue(acc1, p);
+                PHASE_MARK(11);  // log epilogue
+                if (cur.w >= 0) {
+                    float *o = orow + cur.w * p.T;
+                    o[0] = y0;
+                    if (kPair && t.valid1) o[1] = y1;
                 }
-                acc0 += b0, acc1 += b1;
-                if (e.m >= 0) {
-                    float *o = orow + (long long)e.m * p.T;
-                    o[0] = epilogue(acc0, p);
-                    if (kPair && t.valid1) o[1] = epilogue(acc1, p);
-                }
+                PHASE_MARK(12);  // stores
             }
             __syncwarp();  // tile reads done before the next task's transpose overwrites the region
+            PHASE_MARK(13);  // final syncwarp
         }
     }
+#ifdef B200MEL_PHASE_TIMING
+    if (p.dbg && lane == 0) {
+#pragma unroll
+        for (int i_ = 0; i_ < 14; ++i_)
+            atomicAdd(reinterpret_cast<unsigned long long *>(p.dbg) + i_, (unsigned long long)phase_acc_[i_]);
+    }
+#endif
+#if defined(B200MEL_PHASE_TIMING) || defined(B200MEL_SPAN_TIMING)
+    if (p.dbg && lane == 0) {
+        unsigned long long t_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+        atomicMax(reinterpret_cast<unsigned long long *>(p.dbg) + 15, t_);
+    }
+#endif
 }
 
 }  // namespace b200mel
