@@ -28,13 +28,37 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SR, N_FFT, HOP, N_MELS = 22050, 1024, 256, 80
+# BASELINE.json configs.  C2 is the config the metric is quoted on and the default; the others are
+# selectable with --workload for the results table in BASELINE.md (per-GPU shard of the named global batch).
+WORKLOADS = {
+    "C2": dict(sr=22050, n_fft=1024, hop=256, n_mels=80, fmax=8000.0, clips=256, L=22050, cfg=2,
+               name="C2: batch 256 x 1 s @22050 Hz per GPU, n_fft=1024 hop=256 mel=80"),
+    "C3": dict(sr=22050, n_fft=1024, hop=256, n_mels=80, fmax=8000.0, clips=256, L=88200, cfg=3,
+               name="C3: batch 2048 x 4 s @22050 Hz over 8 GPUs = 256 clips per GPU, n_fft=1024 hop=256 mel=80"),
+    "C4": dict(sr=44100, n_fft=2048, hop=512, n_mels=128, fmax=None, clips=16, L=441000, cfg=4,
+               name="C4: batch 128 x 10 s @44100 Hz over 8 GPUs = 16 clips per GPU, n_fft=2048 hop=512 mel=128, fmax=sr/2"),
+    "C5": dict(sr=16000, n_fft=1024, hop=256, n_mels=80, fmax=8000.0, clips=8192, L=8000, cfg=5,
+               name="C5: 1M-clip stream x 0.5 s @16000 Hz in batches of 8192 clips per GPU, n_fft=1024 hop=256 mel=80"),
+}
+SR, N_FFT, HOP, N_MELS, FMAX = 22050, 1024, 256, 80, 8000.0
 B_PER_GPU, L = 256, 22050
 T = 1 + L // HOP
+WORKLOAD_NAME = WORKLOADS["C2"]["name"]
 METRIC = "hours-of-audio/sec mel extraction (22050Hz, n_fft=1024, 80 mels)"
 UNIT = "hours_audio/s"
 HOURS_PER_BATCH = B_PER_GPU * L / SR / 3600.0
 SEED = 20261017 + 1000 * 2
+
+
+def select_workload(key):
+    global SR, N_FFT, HOP, N_MELS, FMAX, B_PER_GPU, L, T, HOURS_PER_BATCH, SEED, WORKLOAD_NAME
+    w = WORKLOADS[key]
+    SR, N_FFT, HOP, N_MELS, FMAX = w["sr"], w["n_fft"], w["hop"], w["n_mels"], w["fmax"]
+    B_PER_GPU, L = w["clips"], w["L"]
+    T = 1 + L // HOP
+    HOURS_PER_BATCH = B_PER_GPU * L / SR / 3600.0
+    SEED = 20261017 + 1000 * w["cfg"]
+    WORKLOAD_NAME = w["name"]
 
 
 def peaks():
@@ -115,12 +139,15 @@ def synth(rank, n_batches):
 
     from oracle import mel_oracle as mo  # synthetic-input generator shared with the tests (not on the timed path)
 
-    base = mo.synth_clips(B_PER_GPU, L, SR, seed=SEED + rank, first_clip=rank * B_PER_GPU)
+    n_base = min(B_PER_GPU, 256)  # 72 distinct sinusoids tiled over larger batches
+    base = mo.synth_clips(n_base, L, SR, seed=SEED + rank, first_clip=rank * B_PER_GPU)
+    if n_base < B_PER_GPU:
+        base = np.tile(base, ((B_PER_GPU + n_base - 1) // n_base, 1))[:B_PER_GPU]
     out = np.empty((n_batches, B_PER_GPU, L), dtype=np.float32)
     rng = np.random.default_rng(SEED + 17 * rank)
     for i in range(n_batches):
         # same sinusoids + 1 % noise, plus fresh 0.1 % noise per buffer (cheap, keeps every buffer distinct)
-        out[i] = base + (0.001 * rng.standard_normal((B_PER_GPU, L))).astype(np.float32)
+        out[i] = base + (0.001 * rng.standard_normal((B_PER_GPU, L), dtype=np.float32))
     return out
 
 
@@ -137,15 +164,15 @@ def cpu_reference_run(steps, warmup, budget_s=100.0, full=True):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     ref = mo.TorchReference(sample_rate=SR, mel_size=N_MELS, n_fft=N_FFT, win_length=N_FFT, hop_length=HOP,
-                            min_db=-50, max_db=30, mel_min=0.0, mel_max=8000.0)
-    x = torch.from_numpy(mo.synth_clips(B_PER_GPU, L, SR, seed=SEED))
+                            min_db=-50, max_db=30, mel_min=0.0, mel_max=FMAX)
+    x = torch.from_numpy(mo.synth_clips(min(B_PER_GPU, 256), L, SR, seed=SEED))
     with torch.no_grad():
-        probe = 16
+        probe = min(16, x.shape[0])
         ref.logmel_conv(x[:probe])
         t0 = time.perf_counter()
         ref.logmel_conv(x[:probe])
         per_clip = (time.perf_counter() - t0) / probe
-        clips = int(max(1, min(B_PER_GPU, budget_s / max(1, steps + warmup) / per_clip)))
+        clips = int(max(1, min(x.shape[0], budget_s / max(1, steps + warmup) / per_clip)))
         for _ in range(warmup):
             ref.logmel_conv(x[:clips])
         t0 = time.perf_counter()
@@ -162,7 +189,7 @@ def cpu_reference_run(steps, warmup, budget_s=100.0, full=True):
                 ref.logmel_stft(x[:clips])
             alt = n_alt * clips * L / SR / 3600.0 / (time.perf_counter() - t1)
     return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{clips} of the {B_PER_GPU} C2 clips per step x {steps} steps, conv-DFT LogMelSpectrogram "
+            "sample": f"{clips} of the {B_PER_GPU} clips of the workload per step x {steps} steps, conv-DFT LogMelSpectrogram "
                       f"op sequence (oracle.TorchReference.logmel_conv), torch {torch.__version__} CPU fp32, "
                       f"{cores} threads",
             "torch_stft_variant_value": alt, "ms_per_step": dt / steps * 1e3, "clips_per_step": clips}
@@ -178,7 +205,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: batch 256 x 1 s @22050 Hz, n_fft=1024 hop=256 mel=80 (bounded sample per step)",
+        "config": {"workload": WORKLOAD_NAME + " (bounded sample per step)",
                    "clips_per_step": r["clips_per_step"]},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -194,7 +221,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    select_workload(args.workload)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -223,10 +252,12 @@ def main():
 
     build.build()
     module = LogMelSpectrogram(sample_rate=SR, mel_size=N_MELS, n_fft=N_FFT, win_length=N_FFT, hop_length=HOP,
-                               min_db=-50, max_db=30, mel_min=0.0, mel_max=8000.0).to(dev)
+                               min_db=-50, max_db=30, mel_min=0.0, mel_max=FMAX).to(dev)
 
     # ---- inputs: NBUF distinct batches, > L2 in aggregate --------------------------------------------
-    NBUF = 8  # 8 x (22.6 MB in + 7.1 MB out) = 238 MB > 126 MB L2
+    # enough distinct buffer pairs to exceed the 126 MB L2 (C2: 8 x (22.6 MB in + 7.1 MB out) = 238 MB)
+    pair_bytes = 4 * B_PER_GPU * (L + N_MELS * T)
+    NBUF = max(2, min(8, -(-200_000_000 // pair_bytes)))
     host = torch.from_numpy(synth(rank, NBUF)).pin_memory()
     d_in = host.to(dev)
     outs = [None] * NBUF
@@ -345,16 +376,15 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: batch 256 x 1 s @22050 Hz per GPU, n_fft=1024 hop=256 mel=80, "
-                                   "LogMelSpectrogram (centre pad, ln(mel+1e-6), clamp -50/30 dB)",
+            "config": {"workload": WORKLOAD_NAME + ", LogMelSpectrogram (centre pad, ln(mel+1e-6), clamp -50/30 dB)",
                        "clips_per_gpu": B_PER_GPU, "samples_per_clip": L, "frames_per_clip": T,
                        "l2_policy": f"rotating over {NBUF} distinct input/output buffer pairs "
                                     f"({NBUF * (bytes_read + bytes_written) / 1e6:.0f} MB > 126 MB L2)",
                        "parallelism": f"clips sharded over {world} GPU(s), no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "basis": "HBM-read (4*B*L bytes per launch)",
+                         "traffic": ncu_traffic() if args.workload == "C2" else None, "peak_source": peak_src, "basis": "HBM-read (4*B*L bytes per launch)",
                          "read_plus_write_frac": (bytes_read + bytes_written) / (ms_per_step * 1e-3) / 1e9 / peak,
-                         "kernel": "b200mel::logmel_kernel<pair, mel, 16 warps>",
+                         "kernel": "b200mel::logmel_kernel<%s, mel, 16 warps>" % ("pair" if N_FFT == 1024 else "split"),
                          "avg_launch_us": ms_per_step * 1e3},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_read,
                     "d2h_bytes_per_step": bytes_written, "ms_per_step": ms_e2e, "steps": e2e_steps,
