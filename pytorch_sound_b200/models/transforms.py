@@ -228,3 +228,62 @@ class MelToMFCC(nn.Module):
     def forward(self, mel_spec: torch.Tensor) -> torch.Tensor:
         assert len(mel_spec.size()) == 3
         return torch.matmul(self.dct_mat, mel_spec)
+
+
+class MFCC(nn.Module):
+    """pytorch_sound.models.transforms.MFCC (transforms.py:433-455): LogMelSpectrogram followed by the ortho DCT.
+
+    The reference asserts a 3-D input but then feeds its 2-D-only STFT; this class takes the
+    (B, L) waveform its LogMelSpectrogram needs (a (B, 1, L) tensor is squeezed)."""
+
+    def __init__(self, sample_rate: int, mel_size: int, n_fft: int, win_length: int, n_mfcc: int,
+                 hop_length: int, min_db: float, max_db: float,
+                 mel_min: float = 0., mel_max: float = None, norm: str = 'ortho'):
+        super().__init__()
+        self.n_mfcc = n_mfcc
+        self.mel_func = LogMelSpectrogram(
+            sample_rate, mel_size, n_fft, win_length, hop_length, min_db, max_db,
+            mel_min, mel_max
+        )
+        self.register_buffer('dct_mat', MelToMFCC(n_mfcc, mel_size, norm).dct_mat.clone())
+
+    def forward(self, wav: torch.Tensor) -> torch.Tensor:
+        if wav.dim() == 3 and wav.shape[1] == 1:
+            wav = wav[:, 0]
+        mel_spectrogram = self.mel_func(wav)
+        return torch.matmul(self.dct_mat, mel_spectrogram)
+
+
+class SpectrogramMasker(nn.Module):
+    """pytorch_sound.models.transforms.SpectrogramMasker (transforms.py:397-416): wave-level validity mask ->
+    frame-level mask with the kernel's frame geometry (T = 1 + L // hop).
+
+    The reference runs a strided mean-filter conv over the mask padded with win//2 ones on the left and win//2
+    zeros on the right and takes ceil(): a frame is 1 iff any sample of its window is valid.  Same result here from
+    one cumulative sum (no conv weights, runs on the mask's device; the reference hard-codes .cuda()).
+    `from_lengths` gives the same frame mask straight from per-clip lengths (the `lengths=` argument of the
+    extractor), without materialising a wave-level mask."""
+
+    def __init__(self, win_length: int, hop_length: int):
+        super().__init__()
+        self.win_length = win_length
+        self.hop_length = hop_length
+
+    def forward(self, wav_mask: torch.Tensor) -> torch.Tensor:
+        with torch.no_grad():
+            half = self.win_length // 2
+            m = wav_mask.float()
+            m = torch.nn.functional.pad(m, [0, half], value=0.)
+            m = torch.nn.functional.pad(m, [half, 0], value=1.)
+            csum = torch.nn.functional.pad(torch.cumsum(m.double(), dim=-1), [1, 0])
+            n_frames = (m.shape[-1] - self.win_length) // self.hop_length + 1
+            start = torch.arange(n_frames, device=m.device) * self.hop_length
+            frame_sum = csum[..., start + self.win_length] - csum[..., start]
+            return (frame_sum > 0).float()
+
+    def from_lengths(self, lengths: torch.Tensor, n_samples: int) -> torch.Tensor:
+        half = self.win_length // 2
+        n_frames = (n_samples + 2 * half - self.win_length) // self.hop_length + 1
+        t = torch.arange(n_frames, device=lengths.device)
+        # frame t covers padded samples [t*hop, t*hop + win) = wave samples [t*hop - half, t*hop - half + win)
+        return ((t * self.hop_length - half) < lengths.view(-1, 1)).float()

@@ -369,3 +369,22 @@ def test_host_pointer_entry_point(torch_cuda, built_lib):
     torch.cuda.synchronize()
     assert mo.parity_error(out.numpy(), mo.log_mel_spectrogram(x, **GEO, clamp=False)) < TOL
     plan.close()
+
+
+def test_mfcc_and_patch(torch_cuda):
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+
+    x = mo.synth_clips(3, 5000, 22050, seed=8)
+    mf = T.MFCC(22050, 80, 1024, 1024, 40, 256, -50, 30, 0.0, 8000.0).cuda()
+    y = mf(cuda(torch, x)).cpu().numpy()
+    ref_mel = mo.log_mel_spectrogram(x, min_db=-50, max_db=30, **GEO)
+    n = np.arange(80)
+    k = np.arange(40)[:, None]
+    dct = np.cos(np.pi / 80 * (n + 0.5) * k)
+    dct[0] *= 1 / np.sqrt(2)
+    dct *= np.sqrt(2 / 80)
+    ref = np.einsum("km,bmt->bkt", dct, ref_mel)
+    assert y.shape == (3, 40, 20)
+    assert np.abs(y - ref).max() < 1e-3  # 80-term sums of log values with |.| <= 11.5, each within 1e-4
+    assert mf(cuda(torch, x).unsqueeze(1)).shape == (3, 40, 20)

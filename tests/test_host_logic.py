@@ -193,3 +193,29 @@ def test_all_gather_mel_world_size_2_gloo(n_clips):
     for p in procs:
         p.join(timeout=60)
     assert results == [(0, True), (1, True)]
+
+
+def test_spectrogram_masker_matches_reference_formula():
+    """Restatement of models/transforms.py:408-416 (mean-filter conv + ceil) vs the cumulative-sum form."""
+    from pytorch_sound_b200.models.transforms import SpectrogramMasker
+
+    win, hop, L = 1024, 256, 6000
+    lens = torch.tensor([6000, 4500, 513, 1, 3000])
+    mask = (torch.arange(L).view(1, -1) < lens.view(-1, 1)).float()
+    # the reference's op sequence on CPU
+    conv = torch.nn.Conv1d(1, 1, win, stride=hop, padding=0, bias=False)
+    torch.nn.init.constant_(conv.weight, 1. / win)
+    with torch.no_grad():
+        m = torch.nn.functional.pad(mask, [0, win // 2], value=0.)
+        m = torch.nn.functional.pad(m, [win // 2, 0], value=1.)
+        ref = torch.ceil(conv(m.unsqueeze(1)).squeeze(1))
+    sm = SpectrogramMasker(win, hop)
+    out = sm(mask)
+    assert out.shape == ref.shape == (5, 1 + L // hop)
+    assert torch.equal(out, ref)
+    assert torch.equal(sm.from_lengths(lens, L), ref)
+    holes = mask.clone()
+    holes[0, 100:5000] = 0  # non-prefix masks work too
+    m = torch.nn.functional.pad(torch.nn.functional.pad(holes, [0, win // 2]), [win // 2, 0], value=1.)
+    with torch.no_grad():
+        assert torch.equal(sm(holes), torch.ceil(conv(m.unsqueeze(1)).squeeze(1)))
