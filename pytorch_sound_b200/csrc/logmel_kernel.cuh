@@ -422,11 +422,22 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
                 }
             } else {
                 const float2 *w2 = reinterpret_cast<const float2 *>(s_win);
+                if ((delta & 1) == 0) {  // warp-uniform: the (even, odd) sample pair is 8-byte aligned -> one LDS.64
+                    const float2 *xp = reinterpret_cast<const float2 *>(stage + delta) + lane;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float2 w = w2[32 * j + lane];
-                    a[j].x = x0[64 * j + lane] * w.x;        // sample 64 j + 2 lane
-                    a[j].y = x0[64 * j + lane + 1] * w.y;    // sample 64 j + 2 lane + 1
+                    for (int j = 0; j < 32; ++j) {
+                        const float2 w = w2[32 * j + lane];
+                        const float2 v = xp[32 * j];
+                        a[j].x = v.x * w.x;
+                        a[j].y = v.y * w.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float2 w = w2[32 * j + lane];
+                        a[j].x = x0[64 * j + lane] * w.x;        // sample 64 j + 2 lane
+                        a[j].y = x0[64 * j + lane + 1] * w.y;    // sample 64 j + 2 lane + 1
+                    }
                 }
             }
 
