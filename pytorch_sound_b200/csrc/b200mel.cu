@@ -32,6 +32,10 @@ namespace b200mel {
 // ----------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
+static const bool g_pdl = [] {  // B200MEL_PDL=0 disables programmatic dependent launch (A/B measurements)
+    const char *e = getenv("B200MEL_PDL");
+    return !(e && e[0] == '0');
+}();
 static long long *g_dbg = nullptr;  // device buffer for -DB200MEL_PHASE_TIMING builds (b200mel_debug_set_buffer)
 
 static int fail(int code, const std::string &msg) {
@@ -528,12 +532,26 @@ int b200mel_forward(const b200mel_plan *pl, const float *wav, int64_t B, int64_t
     p.stride_q = (int)(stride % tpc);
 
     cudaStream_t st = (cudaStream_t)stream;
+    // Launch with programmatic stream serialization (PDL): the kernel's table prologue may overlap the tail of the
+    // previous kernel in the stream; it executes griddepcontrol.wait before touching wav / outputs.
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.dynamicSmemBytes = pl->smem_bytes;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaSuccess;
     // mel and spectrum outputs come from separately specialised kernels (no reference module needs both at once)
     if (out_mel) {
-        pick_kernel(pl->pair, 0, true, pl->cfg.power, pl->n_warps)<<<(unsigned)n_cta, pl->n_warps * 32, pl->smem_bytes, st>>>(p);
+        cfg.gridDim = dim3((unsigned)n_cta);
+        cfg.blockDim = dim3(pl->n_warps * 32);
+        le = cudaLaunchKernelEx(&cfg, pick_kernel(pl->pair, 0, true, pl->cfg.power, pl->n_warps), p);
         g_launches.fetch_add(1);
     }
-    if (spec_kind) {
+    if (spec_kind && le == cudaSuccess) {
         // spectrum kernels are built for <= 16 warps: re-derive the launch shape for them
         const int sw = pl->n_warps > 16 ? 16 : pl->n_warps;
         long long s_cta = (p.n_tasks + sw - 1) / sw;
@@ -541,9 +559,12 @@ int b200mel_forward(const b200mel_plan *pl, const float *wav, int64_t B, int64_t
         const long long s_stride = s_cta * sw;
         p.stride_b = (int)(s_stride / tpc);
         p.stride_q = (int)(s_stride % tpc);
-        pick_kernel(pl->pair, spec_kind, false, 1, sw)<<<(unsigned)s_cta, sw * 32, pl->smem_bytes, st>>>(p);
+        cfg.gridDim = dim3((unsigned)s_cta);
+        cfg.blockDim = dim3(sw * 32);
+        le = cudaLaunchKernelEx(&cfg, pick_kernel(pl->pair, spec_kind, false, 1, sw), p);
         g_launches.fetch_add(1);
     }
+    if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx");
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     return B200MEL_OK;

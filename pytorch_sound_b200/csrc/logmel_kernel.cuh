@@ -296,32 +296,58 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
     long long cb = task / p.tasks_per_clip;
     int cq = (int)(task - cb * p.tasks_per_clip);
 
-    // every warp owns its mbarrier: arm it and get the first task's samples moving before the tables are loaded
+    // Prologue, ordered for programmatic dependent launch (PDL): everything that does not touch caller memory —
+    // mbarrier init and the loads of the plan-owned tables — runs BEFORE griddepcontrol.wait, i.e. it overlaps the
+    // tail of whatever kernel precedes this one in the stream.  Caller memory (wav, outputs) is only touched after
+    // the wait; griddepcontrol.launch_dependents then lets the next launch start its own prologue the same way.
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (task < p.n_tasks) {
-            const Task t = decode_task<kPair>(p, cb, cq);
-            if (t.valid0) issue_stage<kPair>(p, t, stage, bar);
-        }
     }
+    int4 t_tw = make_int4(0, 0, 0, 0), t_win = t_tw, t_ent = t_tw;
+    const int tid = threadIdx.x;  // blockDim.x >= 32: the 512-entry twiddle table takes up to 16 rounds at 1 warp
+    if (blockDim.x >= 512) {
+        t_tw = __ldg(reinterpret_cast<const int4 *>(p.tw) + tid);
+        if (tid < p.n_fft / 4) t_win = __ldg(reinterpret_cast<const int4 *>(p.window) + tid);
+        if (kMel && tid < p.mel_rounds * 32) t_ent = __ldg(reinterpret_cast<const int4 *>(p.mel_entries) + tid);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // every warp gets its first task's samples moving before the tables are stored
+    if (lane == 0 && task < p.n_tasks) {
+        const Task t = decode_task<kPair>(p, cb, cq);
+        if (t.valid0) issue_stage<kPair>(p, t, stage, bar);
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __syncwarp();
     {
         const int4 *g;
         int4 *s;
-        g = reinterpret_cast<const int4 *>(p.tw);
-        s = reinterpret_cast<int4 *>(s_tw);
-        for (int i = threadIdx.x; i < 32 * 32 * 8 / 16; i += blockDim.x) s[i] = __ldg(g + i);
-        g = reinterpret_cast<const int4 *>(p.window);
-        s = reinterpret_cast<int4 *>(s_win);
-        for (int i = threadIdx.x; i < p.n_fft / 4; i += blockDim.x) s[i] = __ldg(g + i);
+        if (blockDim.x >= 512) {
+            reinterpret_cast<int4 *>(s_tw)[tid] = t_tw;
+            if (tid < p.n_fft / 4) reinterpret_cast<int4 *>(s_win)[tid] = t_win;
+            if (kMel && tid < p.mel_rounds * 32) reinterpret_cast<int4 *>(smem_raw + p.off_entries)[tid] = t_ent;
+            if (p.n_fft / 4 > 512) {  // never for n_fft <= 2048; kept generic
+                g = reinterpret_cast<const int4 *>(p.window);
+                s = reinterpret_cast<int4 *>(s_win);
+                for (int i = tid + 512; i < p.n_fft / 4; i += blockDim.x) s[i] = __ldg(g + i);
+            }
+        } else {
+            g = reinterpret_cast<const int4 *>(p.tw);
+            s = reinterpret_cast<int4 *>(s_tw);
+            for (int i = tid; i < 32 * 32 * 8 / 16; i += blockDim.x) s[i] = __ldg(g + i);
+            g = reinterpret_cast<const int4 *>(p.window);
+            s = reinterpret_cast<int4 *>(s_win);
+            for (int i = tid; i < p.n_fft / 4; i += blockDim.x) s[i] = __ldg(g + i);
+            if (kMel) {
+                g = reinterpret_cast<const int4 *>(p.mel_entries);
+                s = reinterpret_cast<int4 *>(smem_raw + p.off_entries);
+                for (int i = tid; i < p.mel_rounds * 32; i += blockDim.x) s[i] = __ldg(g + i);
+            }
+        }
         if (kMel) {
-            g = reinterpret_cast<const int4 *>(p.mel_entries);
-            s = reinterpret_cast<int4 *>(smem_raw + p.off_entries);
-            for (int i = threadIdx.x; i < p.mel_rounds * 32; i += blockDim.x) s[i] = __ldg(g + i);
             g = reinterpret_cast<const int4 *>(p.mel_w);
             s = reinterpret_cast<int4 *>(smem_raw + p.off_melw);
-            for (int i = threadIdx.x; i < p.mel_w_len / 4; i += blockDim.x) s[i] = __ldg(g + i);
+            for (int i = tid; i < p.mel_w_len / 4; i += blockDim.x) s[i] = __ldg(g + i);
         }
     }
     __syncthreads();  // the only block-wide barrier; warps are independent from here on
