@@ -24,6 +24,7 @@
 #include "../../include/b200mel.h"
 #include "fft32.cuh"
 #include "logmel_kernel.cuh"
+#include "spec_kernel.cuh"
 
 namespace b200mel {
 
@@ -116,6 +117,8 @@ struct b200mel_plan {
     // shared-memory layout
     int off_window = 0, off_entries = 0, off_melw = 0, off_bar = 0, off_regions = 0, region_bytes = 0, stage_bytes = 0;
     int n_warps = 0, smem_bytes = 0;
+    // spectrum-output kernel (spec_kernel.cuh): tw | window | mbarriers | slots | 8 warp regions | tile A | tile B
+    int sp_off_bar = 0, sp_off_slots = 0, sp_off_regions = 0, sp_off_tiles = 0, sp_smem_bytes = 0;
     // staging for forward_host
     float *d_stage_in = nullptr, *d_stage_out = nullptr;
     size_t stage_in_bytes = 0, stage_out_bytes = 0;
@@ -155,6 +158,15 @@ static int layout_smem(b200mel_plan *pl) {
         return fail(B200MEL_EUNSUP, "plan: hop_length / filterbank too large for the shared-memory staging of this build");
     pl->n_warps = n_warps;
     pl->smem_bytes = pl->off_regions + n_warps * pl->region_bytes;
+    // spectrum-output kernel
+    const int cols = pl->pair ? 2 * kSpecWarps : kSpecWarps;
+    pl->sp_off_bar = pl->off_window + n_fft * 4;
+    pl->sp_off_slots = pl->sp_off_bar + kSpecWarps * 8;
+    pl->sp_off_regions = (pl->sp_off_slots + kSpecWarps * (int)sizeof(SpecSlot) + 127) & ~127;
+    pl->sp_off_tiles = pl->sp_off_regions + kSpecWarps * pl->region_bytes;
+    pl->sp_smem_bytes = pl->sp_off_tiles + 2 * pl->n_freq * (cols + 1) * 4;
+    if (pl->sp_smem_bytes > kMaxSmem)
+        return fail(B200MEL_EUNSUP, "plan: hop_length too large for the shared-memory staging of the spectrum kernel");
     return B200MEL_OK;
 }
 
@@ -269,7 +281,7 @@ static int upload_filterbank(b200mel_plan *pl, const float *W, int n_mels, int F
 
 typedef void (*kernel_fn)(const KParams);
 // The mel kernels exist in 16 / 20 / 24-warp builds (128 / 96 / 80 registers per thread); the spectrum-output
-// kernels are store-bound and only built for 16 warps.
+// operators use the 8-warp cooperative kernel of spec_kernel.cuh.
 template <int kWarps>
 static kernel_fn pick_mel_kernel(bool pair, int power) {
     if (pair) return power == 2 ? logmel_kernel<true, 0, true, 2, kWarps> : logmel_kernel<true, 0, true, 1, kWarps>;
@@ -282,12 +294,9 @@ static kernel_fn pick_kernel(bool pair, int spec, bool mel, int power, int warps
         return pick_mel_kernel<16>(pair, power);
     }
     switch (spec) {
-        case B200MEL_SPEC_MAG_PHASE:
-            return pair ? logmel_kernel<true, 1, false, 1, 16> : logmel_kernel<false, 1, false, 1, 16>;
-        case B200MEL_SPEC_RE_IM:
-            return pair ? logmel_kernel<true, 2, false, 1, 16> : logmel_kernel<false, 2, false, 1, 16>;
-        default:
-            return pair ? logmel_kernel<true, 3, false, 1, 16> : logmel_kernel<false, 3, false, 1, 16>;
+        case B200MEL_SPEC_MAG_PHASE: return pair ? spec_kernel<true, 1> : spec_kernel<false, 1>;
+        case B200MEL_SPEC_RE_IM: return pair ? spec_kernel<true, 2> : spec_kernel<false, 2>;
+        default: return pair ? spec_kernel<true, 3> : spec_kernel<false, 3>;
     }
 }
 
@@ -552,16 +561,20 @@ int b200mel_forward(const b200mel_plan *pl, const float *wav, int64_t B, int64_t
         g_launches.fetch_add(1);
     }
     if (spec_kind && le == cudaSuccess) {
-        // spectrum kernels are built for <= 16 warps: re-derive the launch shape for them
-        const int sw = pl->n_warps > 16 ? 16 : pl->n_warps;
-        long long s_cta = (p.n_tasks + sw - 1) / sw;
+        // cooperative 8-warp kernel with its own shared-memory carve-up and launch shape
+        long long s_cta = (p.n_tasks + kSpecWarps - 1) / kSpecWarps;
         if (s_cta > pl->num_sms) s_cta = pl->num_sms;
-        const long long s_stride = s_cta * sw;
+        const long long s_stride = s_cta * kSpecWarps;
         p.stride_b = (int)(s_stride / tpc);
         p.stride_q = (int)(s_stride % tpc);
+        p.off_bar = pl->sp_off_bar;
+        p.off_entries = pl->sp_off_slots;
+        p.off_regions = pl->sp_off_regions;
+        p.off_melw = pl->sp_off_tiles;
         cfg.gridDim = dim3((unsigned)s_cta);
-        cfg.blockDim = dim3(sw * 32);
-        le = cudaLaunchKernelEx(&cfg, pick_kernel(pl->pair, spec_kind, false, 1, sw), p);
+        cfg.blockDim = dim3(kSpecWarps * 32);
+        cfg.dynamicSmemBytes = pl->sp_smem_bytes;
+        le = cudaLaunchKernelEx(&cfg, pick_kernel(pl->pair, spec_kind, false, 1, kSpecWarps), p);
         g_launches.fetch_add(1);
     }
     if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx");

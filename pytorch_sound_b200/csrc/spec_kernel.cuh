@@ -1,0 +1,236 @@
+// spec_kernel.cuh — spectrum-output variant of the fused STFT kernel (sm_100a): STFT.transform (mag, phase),
+// STFTTorchAudio.forward (re, im) and magnitude-only.  Replaces models/transforms.py:53-69 and :297-311.
+//
+// These operators write (B, n_fft/2+1, T) tensors — 6.4x (one array) to 12.8x (two arrays) the bytes of the
+// mel output — so they are bound by how well the stores coalesce, not by the FFT.  A warp only ever holds two
+// frames of a bin (8 contiguous bytes of an output row); the 8 warps of a CTA therefore work in lock step on 8
+// CONSECUTIVE tasks (16 consecutive frames of a clip in pair mode) and pool their spectra in a CTA-wide shared
+// tile [bin][frame column], which the whole CTA then writes out row-wise: 16 consecutive threads store 64
+// contiguous bytes of one output row.
+//
+// FFT pipeline per warp identical to logmel_kernel.cuh (TMA stage -> window -> radix-32 pass -> transpose +
+// twiddle -> radix-32 pass -> real-input separation); see there for the index algebra.
+#pragma once
+#include "logmel_kernel.cuh"
+
+namespace b200mel {
+
+constexpr int kSpecWarps = 8;
+
+struct SpecSlot {  // where the columns of one warp's task go (written by lane 0 of the warp every round)
+    long long row0;  // element offset of (clip b, bin 0, frame t0) in the output arrays
+    int n_frames;    // valid frames of the task (0 = idle slot, 1, or 2 in pair mode)
+    int zero;        // 1: the task lies past the clip's own end (lengths) -> its columns are written as zeros
+};
+
+// atan2 with ~3e-7 rad absolute error (degree-7 minimax polynomial in t^2 on [0,1], octant reduction, one
+// MUFU.RCP); the library atan2f costs about twice the instructions and dominated the mag+phase kernel.
+__device__ __forceinline__ float fast_atan2(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float t = mx > 0.f ? __fdividef(mn, mx) : 0.f;
+    const float s = t * t;
+    float r = -0.004054528195410967f;
+    r = fmaf(r, s, 0.021862806752324104f);
+    r = fmaf(r, s, -0.055912092328071594f);
+    r = fmaf(r, s, 0.09642178565263748f);
+    r = fmaf(r, s, -0.13908621668815613f);
+    r = fmaf(r, s, 0.19946563243865967f);
+    r = fmaf(r, s, -0.33329859375953674f);
+    r = fmaf(r, s, 0.9999993443489075f);
+    r *= t;
+    if (ay > ax) r = 1.57079632679489662f - r;
+    if (x < 0.f) r = 3.14159265358979324f - r;
+    return copysignf(r, y);
+}
+
+template <int kSpec>
+__device__ __forceinline__ void spec_deposit(float *ta, float *tb, int idx, float re, float im, float eps) {
+    if constexpr (kSpec == B200MEL_SPEC_RE_IM) {
+        ta[idx] = re;
+        tb[idx] = im;
+    } else {
+        ta[idx] = sqrt_approx(fmaf(re, re, im * im) + eps);
+        if constexpr (kSpec == B200MEL_SPEC_MAG_PHASE) tb[idx] = fast_atan2(im, re);
+    }
+}
+
+// Shared layout (bytes): tw 8192 | window 4 n_fft | mbarriers | slots | 8 warp regions | tile A | tile B
+template <bool kPair, int kSpec>
+__global__ void __launch_bounds__(kSpecWarps * 32, 1) spec_kernel(const KParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    constexpr int kCols = kPair ? 2 * kSpecWarps : kSpecWarps;  // frame columns of the CTA tile
+    constexpr int kRowStride = kCols + 1;                      // odd stride: conflict-free deposits and row reads
+    constexpr bool kTwo = kSpec != B200MEL_SPEC_MAG;
+
+    float2 *s_tw = reinterpret_cast<float2 *>(smem_raw);
+    float *s_win = reinterpret_cast<float *>(smem_raw + p.off_window);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + p.off_bar);
+    SpecSlot *s_slot = reinterpret_cast<SpecSlot *>(smem_raw + p.off_entries);
+    unsigned char *region = smem_raw + p.off_regions + warp * p.region_bytes;
+    float2 *buf = reinterpret_cast<float2 *>(region);
+    float *stage = reinterpret_cast<float *>(region + kStageOff);
+    float *tile_a = reinterpret_cast<float *>(smem_raw + p.off_melw);
+    float *tile_b = tile_a + p.n_freq * kRowStride;
+    const uint32_t bar = smem_u32(s_bar + warp);
+    uint32_t parity = 0;
+
+    const long long stride = (long long)gridDim.x * kSpecWarps;
+    long long task = (long long)blockIdx.x * kSpecWarps + warp;
+    long long cb = task / p.tasks_per_clip;
+    int cq = (int)(task - cb * p.tasks_per_clip);
+
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < 32 * 32 * 8 / 16; i += blockDim.x)
+        reinterpret_cast<int4 *>(s_tw)[i] = __ldg(reinterpret_cast<const int4 *>(p.tw) + i);
+    for (int i = tid; i < p.n_fft / 4; i += blockDim.x)
+        reinterpret_cast<int4 *>(s_win)[i] = __ldg(reinterpret_cast<const int4 *>(p.window) + i);
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: caller memory is only touched below this line
+    if (lane == 0 && task < p.n_tasks) {
+        const Task t = decode_task<kPair>(p, cb, cq);
+        if (t.valid0) issue_stage<kPair>(p, t, stage, bar);
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    __syncthreads();
+
+    float2 wl = make_float2(1.f, 0.f);
+    if (!kPair) wl = __ldg(p.tw_post + lane);
+
+    // all warps of the CTA run the same number of rounds (idle warps still join the barriers)
+    for (long long base = (long long)blockIdx.x * kSpecWarps; base < p.n_tasks; base += stride, task += stride) {
+        const bool have = task < p.n_tasks;
+        Task t;
+        t.valid0 = t.valid1 = false;
+        if (have) {
+            t = decode_task<kPair>(p, cb, cq);
+            cb += p.stride_b;
+            cq += p.stride_q;
+            if (cq >= p.tasks_per_clip) cq -= p.tasks_per_clip, ++cb;
+        }
+        float2 a[32];
+        if (t.valid0) {
+            const float *row = p.wav + t.b * p.row_stride;
+            const int delta = stage_delta(row, t);
+            mbar_wait(bar, parity);
+            parity ^= 1;
+            if (t.s_first < 0 || t.s_first + t.span > t.Li) {
+                for (int i = lane; i < t.span; i += 32) {
+                    const int s = t.s_first + i;
+                    if (s < 0 || s >= t.Li) stage[i + delta] = __ldg(row + reflect_index(s, t.Li));
+                }
+                __syncwarp();
+            }
+            const float *x0 = stage + delta + lane;
+            if (kPair) {
+                const float *x1 = x0 + (t.valid1 ? p.hop : 0);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float w = s_win[32 * j + lane];
+                    a[j].x = x0[32 * j] * w;
+                    a[j].y = t.valid1 ? x1[32 * j] * w : 0.f;
+                }
+            } else {
+                const float2 *w2 = reinterpret_cast<const float2 *>(s_win);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float2 w = w2[32 * j + lane];
+                    a[j].x = x0[64 * j + lane] * w.x;
+                    a[j].y = x0[64 * j + lane + 1] * w.y;
+                }
+            }
+            fft32(a);
+            __syncwarp();
+            static_for<0, 32>([&](auto k1_) {
+                constexpr int k1 = decltype(k1_)::value;
+                buf[k1 * kBufStride + lane] = a[fft32_pos(k1)];
+            });
+            __syncwarp();
+            static_for<0, 2>([&](auto h_) {
+                constexpr int h = decltype(h_)::value;
+                float2 tw[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) a[h * 16 + i] = buf[lane * kBufStride + h * 16 + i];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) tw[i] = s_tw[(h * 16 + i) * 32 + lane];
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (h * 16 + i > 0) a[h * 16 + i] = cmul(a[h * 16 + i], tw[i]);
+            });
+            __syncwarp();
+        }
+        // prefetch this warp's next task (its task index is task + stride)
+        if (lane == 0 && task + stride < p.n_tasks) {
+            const Task n = decode_task<kPair>(p, cb, cq);
+            if (n.valid0) issue_stage<kPair>(p, n, stage, bar);
+        }
+        if (lane == 0) {
+            SpecSlot s;
+            s.n_frames = have ? (kPair && p.pair_frames == 2 ? (t.t0 + 1 < p.T ? 2 : 1) : 1) : 0;
+            s.zero = have && !t.valid0;
+            s.row0 = have ? (t.b * p.n_freq) * (long long)p.T + t.t0 : 0;
+            if (have && kPair && p.pair_frames == 2 && t.valid0 && !t.valid1 && t.t0 + 1 < p.T) s.zero = 2;  // second frame only
+            s_slot[warp] = s;
+        }
+        if (t.valid0) {
+            fft32(a);
+            const int partner = (32 - lane) & 31;
+            const int col = kPair ? 2 * warp : warp;
+            static_for<0, 16>([&](auto k2_) {
+                constexpr int k2 = decltype(k2_)::value;
+                const float2 A = a[fft32_pos(k2)];
+                const float2 g0 = a[fft32_pos((32 - k2) & 31)];
+                const float2 g1 = a[fft32_pos(31 - k2)];
+                float2 Bv;
+                Bv.x = __shfl_sync(0xffffffffu, lane == 0 ? g0.x : g1.x, partner);
+                Bv.y = __shfl_sync(0xffffffffu, lane == 0 ? g0.y : g1.y, partner);
+                const int k = lane + 32 * k2;
+                const float2 E = make_float2(A.x + Bv.x, A.y - Bv.y);
+                const float2 O = make_float2(A.y + Bv.y, Bv.x - A.x);
+                if constexpr (kPair) {
+                    spec_deposit<kSpec>(tile_a, tile_b, k * kRowStride + col, E.x, E.y, p.mag_eps);
+                    spec_deposit<kSpec>(tile_a, tile_b, k * kRowStride + col + 1, O.x, O.y, p.mag_eps);
+                } else {
+                    constexpr float w64c = TwConst::c64[k2], w64s = TwConst::s64[k2];
+                    const float2 P = cmul(O, cmul(wl, make_float2(w64c, w64s)));
+                    const float2 X0 = cadd(E, P), X1 = csub(E, P);
+                    spec_deposit<kSpec>(tile_a, tile_b, k * kRowStride + col, X0.x, X0.y, p.mag_eps);
+                    spec_deposit<kSpec>(tile_a, tile_b, (1024 - k) * kRowStride + col, X1.x, -X1.y, p.mag_eps);
+                }
+            });
+            if (lane == 0) {
+                const float2 A = a[fft32_pos(16)];
+                if constexpr (kPair) {
+                    spec_deposit<kSpec>(tile_a, tile_b, 512 * kRowStride + col, 2.f * A.x, 0.f, p.mag_eps);
+                    spec_deposit<kSpec>(tile_a, tile_b, 512 * kRowStride + col + 1, 2.f * A.y, 0.f, p.mag_eps);
+                } else {
+                    spec_deposit<kSpec>(tile_a, tile_b, 512 * kRowStride + col, 2.f * A.x, -2.f * A.y, p.mag_eps);
+                }
+            }
+        }
+        __syncthreads();  // every warp's columns (and slot records) are in the tile
+
+        // ------------------------------------------------------------------ cooperative row-wise write-out
+        {
+            const int col = tid % kCols, r0 = tid / kCols;
+            constexpr int kRowsPerPass = kSpecWarps * 32 / kCols;
+            const SpecSlot s = s_slot[kPair ? col >> 1 : col];
+            const int f = kPair ? col & 1 : 0;
+            if (f < s.n_frames) {
+                const bool zero = s.zero == 1 || (s.zero == 2 && f == 1);
+                const long long off = s.row0 + f;
+                for (int r = r0; r < p.n_freq; r += kRowsPerPass) {
+                    const long long o = off + (long long)r * p.T;
+                    p.out_a[o] = zero ? 0.f : tile_a[r * kRowStride + col];
+                    if constexpr (kTwo) p.out_b[o] = zero ? 0.f : tile_b[r * kRowStride + col];
+                }
+            }
+        }
+        __syncthreads();  // tile may be overwritten by the next round
+    }
+}
+
+}  // namespace b200mel
