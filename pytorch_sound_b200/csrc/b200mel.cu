@@ -284,8 +284,8 @@ typedef void (*kernel_fn)(const KParams);
 // operators use the 8-warp cooperative kernel of spec_kernel.cuh.
 template <int kWarps>
 static kernel_fn pick_mel_kernel(bool pair, int power) {
-    if (pair) return power == 2 ? logmel_kernel<true, 0, true, 2, kWarps> : logmel_kernel<true, 0, true, 1, kWarps>;
-    return power == 2 ? logmel_kernel<false, 0, true, 2, kWarps> : logmel_kernel<false, 0, true, 1, kWarps>;
+    if (pair) return power == 2 ? logmel_kernel<true, 2, kWarps> : logmel_kernel<true, 1, kWarps>;
+    return power == 2 ? logmel_kernel<false, 2, kWarps> : logmel_kernel<false, 1, kWarps>;
 }
 static kernel_fn pick_kernel(bool pair, int spec, bool mel, int power, int warps) {
     if (mel) {

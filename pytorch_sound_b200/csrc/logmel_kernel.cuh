@@ -239,31 +239,30 @@ template <bool kPair, int kMaxChunk>
 __device__ __forceinline__ void mel_groups(int groups, const float4 *w4, const unsigned char *tile_at_lo, float &acc0,
                                            float &acc1) {
     constexpr int kBytesPerGroup = kPair ? 32 : 16;  // tile bytes one weight group covers
-    if constexpr (kMaxChunk >= 8) {
-        while (groups >= 8) {
-            mel_round<kPair, 8>(w4, tile_at_lo, acc0, acc1);
-            groups -= 8, w4 += 8 * 32, tile_at_lo += 8 * kBytesPerGroup;
-        }
-    } else {
-        while (groups >= 8) {
+    while (groups >= kMaxChunk) {
+        mel_round<kPair, kMaxChunk>(w4, tile_at_lo, acc0, acc1);
+        groups -= kMaxChunk, w4 += kMaxChunk * 32, tile_at_lo += kMaxChunk * kBytesPerGroup;
+    }
+    if constexpr (kMaxChunk > 4) {
+        if (groups & 4) {
             mel_round<kPair, 4>(w4, tile_at_lo, acc0, acc1);
-            groups -= 4, w4 += 4 * 32, tile_at_lo += 4 * kBytesPerGroup;
+            w4 += 4 * 32, tile_at_lo += 4 * kBytesPerGroup;
         }
     }
-    if (groups & 4) {
-        mel_round<kPair, 4>(w4, tile_at_lo, acc0, acc1);
-        w4 += 4 * 32, tile_at_lo += 4 * kBytesPerGroup;
+    if constexpr (kMaxChunk > 2) {
+        if (groups & 2) {
+            mel_round<kPair, 2>(w4, tile_at_lo, acc0, acc1);
+            w4 += 2 * 32, tile_at_lo += 2 * kBytesPerGroup;
+        }
     }
-    if (groups & 2) {
-        mel_round<kPair, 2>(w4, tile_at_lo, acc0, acc1);
-        w4 += 2 * 32, tile_at_lo += 2 * kBytesPerGroup;
+    if constexpr (kMaxChunk > 1) {
+        if (groups & 1) mel_round<kPair, 1>(w4, tile_at_lo, acc0, acc1);
     }
-    if (groups & 1) mel_round<kPair, 1>(w4, tile_at_lo, acc0, acc1);
 }
 
-// kSpec: B200MEL_SPEC_* ; kMel: apply the filterbank + epilogue ; kPower: 1 magnitude, 2 power
-// kWarps: warps per CTA the variant is compiled for (register budget = 65536 / (32 kWarps))
-template <bool kPair, int kSpec, bool kMel, int kPower, int kWarps>
+// kPower: 1 magnitude, 2 power.  kWarps: warps per CTA the variant is compiled for (register budget =
+// 65536 / (32 kWarps)).
+template <bool kPair, int kPower, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -276,7 +275,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
     }
 #endif
 
-    // ------------------------------------------------------------------ CTA tables -> shared memory
     float2 *s_tw = reinterpret_cast<float2 *>(smem_raw);
     float *s_win = reinterpret_cast<float *>(smem_raw + p.off_window);
     const MelEntry *s_ent = reinterpret_cast<const MelEntry *>(smem_raw + p.off_entries);
@@ -305,11 +303,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     int4 t_tw = make_int4(0, 0, 0, 0), t_win = t_tw, t_ent = t_tw;
-    const int tid = threadIdx.x;  // blockDim.x >= 32: the 512-entry twiddle table takes up to 16 rounds at 1 warp
+    const int tid = threadIdx.x;
     if (blockDim.x >= 512) {
         t_tw = __ldg(reinterpret_cast<const int4 *>(p.tw) + tid);
         if (tid < p.n_fft / 4) t_win = __ldg(reinterpret_cast<const int4 *>(p.window) + tid);
-        if (kMel && tid < p.mel_rounds * 32) t_ent = __ldg(reinterpret_cast<const int4 *>(p.mel_entries) + tid);
+        if (tid < p.mel_rounds * 32) t_ent = __ldg(reinterpret_cast<const int4 *>(p.mel_entries) + tid);
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     // every warp gets its first task's samples moving before the tables are stored
@@ -325,12 +323,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
         if (blockDim.x >= 512) {
             reinterpret_cast<int4 *>(s_tw)[tid] = t_tw;
             if (tid < p.n_fft / 4) reinterpret_cast<int4 *>(s_win)[tid] = t_win;
-            if (kMel && tid < p.mel_rounds * 32) reinterpret_cast<int4 *>(smem_raw + p.off_entries)[tid] = t_ent;
-            if (p.n_fft / 4 > 512) {  // never for n_fft <= 2048; kept generic
-                g = reinterpret_cast<const int4 *>(p.window);
-                s = reinterpret_cast<int4 *>(s_win);
-                for (int i = tid + 512; i < p.n_fft / 4; i += blockDim.x) s[i] = __ldg(g + i);
-            }
+            if (tid < p.mel_rounds * 32) reinterpret_cast<int4 *>(smem_raw + p.off_entries)[tid] = t_ent;
+            g = reinterpret_cast<const int4 *>(p.window);
+            s = reinterpret_cast<int4 *>(s_win);
+            for (int i = tid + 512; i < p.n_fft / 4; i += blockDim.x) s[i] = __ldg(g + i);  // n_fft > 2048 only
         } else {
             g = reinterpret_cast<const int4 *>(p.tw);
             s = reinterpret_cast<int4 *>(s_tw);
@@ -338,17 +334,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
             g = reinterpret_cast<const int4 *>(p.window);
             s = reinterpret_cast<int4 *>(s_win);
             for (int i = tid; i < p.n_fft / 4; i += blockDim.x) s[i] = __ldg(g + i);
-            if (kMel) {
-                g = reinterpret_cast<const int4 *>(p.mel_entries);
-                s = reinterpret_cast<int4 *>(smem_raw + p.off_entries);
-                for (int i = tid; i < p.mel_rounds * 32; i += blockDim.x) s[i] = __ldg(g + i);
-            }
+            g = reinterpret_cast<const int4 *>(p.mel_entries);
+            s = reinterpret_cast<int4 *>(smem_raw + p.off_entries);
+            for (int i = tid; i < p.mel_rounds * 32; i += blockDim.x) s[i] = __ldg(g + i);
         }
-        if (kMel) {
-            g = reinterpret_cast<const int4 *>(p.mel_w);
-            s = reinterpret_cast<int4 *>(smem_raw + p.off_melw);
-            for (int i = tid; i < p.mel_w_len / 4; i += blockDim.x) s[i] = __ldg(g + i);
-        }
+        g = reinterpret_cast<const int4 *>(p.mel_w);
+        s = reinterpret_cast<int4 *>(smem_raw + p.off_melw);
+        for (int i = tid; i < p.mel_w_len / 4; i += blockDim.x) s[i] = __ldg(g + i);
     }
     __syncthreads();  // the only block-wide barrier; warps are independent from here on
 
@@ -370,6 +362,24 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
         atomicMax(reinterpret_cast<unsigned long long *>(p.dbg) + 17, t_);   // last warp past the prologue
     }
 #endif
+
+    // Wait for a task's staged samples and patch its reflected halo (edge tasks only: the out-of-range part of the
+    // span is overwritten after the bulk copy has landed).  Returns the stage shift delta.
+    auto acquire_stage = [&](const Task &tk) -> int {
+        const float *row = p.wav + tk.b * p.row_stride;
+        const int delta = stage_delta(row, tk);
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        if (tk.s_first < 0 || tk.s_first + tk.span > tk.Li) {
+            for (int i = lane; i < tk.span; i += 32) {
+                const int s = tk.s_first + i;
+                if (s < 0 || s >= tk.Li) stage[i + delta] = __ldg(row + reflect_index(s, tk.Li));
+            }
+            __syncwarp();
+        }
+        return delta;
+    };
+
     for (; task < p.n_tasks; task += stride) {
         const Task t = decode_task<kPair>(p, cb, cq);
         // next task of this warp
@@ -381,57 +391,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
         float2 a[32];
 
         if (t.valid0) {
-            const float *row = p.wav + b * p.row_stride;
-            const int delta = stage_delta(row, t);
             PHASE_MARK(1);  // decode
-            mbar_wait(bar, parity);
-            parity ^= 1;
-            PHASE_MARK(2);  // wait for the TMA stage
-            // -------------------------------------------------------------- halo (reflect) fix-up, edge tasks only
-            if (t.s_first < 0 || t.s_first + t.span > t.Li) {
-                for (int i = lane; i < t.span; i += 32) {
-                    const int s = t.s_first + i;
-                    if (s < 0 || s >= t.Li) stage[i + delta] = __ldg(row + reflect_index(s, t.Li));
-                }
-                __syncwarp();
-            }
             // -------------------------------------------------------------- stage -> registers, windowed
-            const float *x0 = stage + delta + lane;
-            if (kPair) {
-                if (t.valid1 && p.hop == 256) {
-                    // hop = 8 * 32: element j of frame t+1 IS element j+8 of frame t in the stage, so the two frames
-                    // need 40 distinct shared-memory loads per lane instead of 64
-                    if constexpr (kWarps > 16) {  // two halves: 24 loads in flight instead of 40
-                        float raw[24];
-#pragma unroll
-                        for (int j = 0; j < 24; ++j) raw[j] = x0[32 * j];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float w = s_win[32 * j + lane];
-                            a[j].x = raw[j] * w;
-                            a[j].y = raw[j + 8] * w;
-                        }
-                        float raw2[24];
-#pragma unroll
-                        for (int j = 0; j < 24; ++j) raw2[j] = x0[32 * (j + 16)];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float w = s_win[32 * (j + 16) + lane];
-                            a[j + 16].x = raw2[j] * w;
-                            a[j + 16].y = raw2[j + 8] * w;
-                        }
-                    } else {
-                        float raw[40];
-#pragma unroll
-                        for (int j = 0; j < 40; ++j) raw[j] = x0[32 * j];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float w = s_win[32 * j + lane];
-                            a[j].x = raw[j] * w;
-                            a[j].y = raw[j + 8] * w;
-                        }
-                    }
-                } else if (t.valid1) {
+            const float *x0 = stage + acquire_stage(t) + lane;
+            PHASE_MARK(2);  // wait for the TMA stage
+            if constexpr (kPair) {
+                if (t.valid1) {
                     const float *x1 = x0 + p.hop;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -448,27 +413,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
                 }
             } else {
                 const float2 *w2 = reinterpret_cast<const float2 *>(s_win);
-                if ((delta & 1) == 0) {  // warp-uniform: the (even, odd) sample pair is 8-byte aligned -> one LDS.64
-                    const float2 *xp = reinterpret_cast<const float2 *>(stage + delta) + lane;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float2 w = w2[32 * j + lane];
-                        const float2 v = xp[32 * j];
-                        a[j].x = v.x * w.x;
-                        a[j].y = v.y * w.y;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float2 w = w2[32 * j + lane];
-                        a[j].x = x0[64 * j + lane] * w.x;        // sample 64 j + 2 lane
-                        a[j].y = x0[64 * j + lane + 1] * w.y;    // sample 64 j + 2 lane + 1
-                    }
+                for (int j = 0; j < 32; ++j) {
+                    const float2 w = w2[32 * j + lane];
+                    a[j].x = x0[64 * j + lane] * w.x;        // sample 64 j + 2 lane
+                    a[j].y = x0[64 * j + lane + 1] * w.y;    // sample 64 j + 2 lane + 1
                 }
             }
 
             // -------------------------------------------------------------- 1024-point complex FFT
-            PHASE_MARK(3);  // halo + stage -> registers (windowed)
+            PHASE_MARK(3);  // stage -> registers (windowed)
             fft32(a);  // pass 1: lane = n2, FFT over n1 -> Y[k1] at a[pos(k1)]
             PHASE_MARK(4);  // pass 1
             __syncwarp();  // every lane has consumed the stage before the transpose buffer overwrites it
@@ -478,8 +432,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
             });
             __syncwarp();
             // read back transposed (lane = k1, slot = n2) and apply the inter-pass twiddle W_1024^{n2 k1} on the
-            // read side: the a[] registers are free here, so each half issues its 16 + 16 loads back to back
-            // (deep memory-level parallelism) instead of serialising load -> multiply -> store per element.
+            // read side: the a[] registers are free here, so each batch issues its loads back to back (deep
+            // memory-level parallelism) instead of serialising load -> multiply -> store per element.
             {
                 constexpr int kB = kWarps > 16 ? 8 : 16;  // loads in flight per batch (register budget of the variant)
                 static_for<0, 32 / kB>([&](auto h_) {
@@ -499,12 +453,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
         }
 
         // ------------------------------------------------------------------ prefetch the next task's samples
-        {
-            const long long nt = task + stride;
-            if (nt < p.n_tasks && lane == 0) {
-                const Task n = decode_task<kPair>(p, cb, cq);
-                if (n.valid0) issue_stage<kPair>(p, n, stage, bar);
-            }
+        Task nxt;
+        nxt.valid0 = false;
+        if (task + stride < p.n_tasks) {
+            nxt = decode_task<kPair>(p, cb, cq);
+            if (nxt.valid0 && lane == 0) issue_stage<kPair>(p, nxt, stage, bar);
         }
 
         if (t.valid0) {
@@ -529,85 +482,28 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
                 const float2 E = make_float2(A.x + Bv.x, A.y - Bv.y);
                 const float2 O = make_float2(A.y + Bv.y, Bv.x - A.x);
                 if constexpr (kPair) {
-                    const float m0 = magnitude<kPower>(E.x, E.y, p.mag_eps);
-                    const float m1 = magnitude<kPower>(O.x, O.y, p.mag_eps);
-                    if constexpr (kMel) tile2[k] = make_float2(m0, m1);
-                    if constexpr (kSpec != B200MEL_SPEC_NONE) {
-                        const long long o = (b * p.n_freq + k) * (long long)p.T + t0;
-                        if constexpr (kSpec == B200MEL_SPEC_RE_IM) {
-                            p.out_a[o] = E.x;
-                            p.out_b[o] = E.y;
-                            if (t.valid1) p.out_a[o + 1] = O.x, p.out_b[o + 1] = O.y;
-                        } else {
-                            p.out_a[o] = m0;
-                            if (t.valid1) p.out_a[o + 1] = m1;
-                            if constexpr (kSpec == B200MEL_SPEC_MAG_PHASE) {
-                                p.out_b[o] = atan2f(E.y, E.x);
-                                if (t.valid1) p.out_b[o + 1] = atan2f(O.y, O.x);
-                            }
-                        }
-                    }
+                    tile2[k] = make_float2(magnitude<kPower>(E.x, E.y, p.mag_eps), magnitude<kPower>(O.x, O.y, p.mag_eps));
                 } else {
                     // X[k] = E + W_2048^k O,  X[1024-k] = conj(E - W_2048^k O),  W_2048^k = wl * W_64^{k2}
                     constexpr float w64c = TwConst::c64[k2], w64s = TwConst::s64[k2];
                     const float2 P = cmul(O, cmul(wl, make_float2(w64c, w64s)));
                     const float2 X0 = cadd(E, P), X1 = csub(E, P);
-                    const float m0 = magnitude<kPower>(X0.x, X0.y, p.mag_eps);
-                    const float m1 = magnitude<kPower>(X1.x, X1.y, p.mag_eps);
-                    if constexpr (kMel) {
-                        tile1[k] = m0;
-                        tile1[1024 - k] = m1;
-                    }
-                    if constexpr (kSpec != B200MEL_SPEC_NONE) {
-                        const long long o0 = (b * p.n_freq + k) * (long long)p.T + t0;
-                        const long long o1 = (b * p.n_freq + (1024 - k)) * (long long)p.T + t0;
-                        if constexpr (kSpec == B200MEL_SPEC_RE_IM) {
-                            p.out_a[o0] = X0.x, p.out_b[o0] = X0.y;
-                            p.out_a[o1] = X1.x, p.out_b[o1] = -X1.y;
-                        } else {
-                            p.out_a[o0] = m0, p.out_a[o1] = m1;
-                            if constexpr (kSpec == B200MEL_SPEC_MAG_PHASE) {
-                                p.out_b[o0] = atan2f(X0.y, X0.x);
-                                p.out_b[o1] = atan2f(-X1.y, X1.x);
-                            }
-                        }
-                    }
+                    tile1[k] = magnitude<kPower>(X0.x, X0.y, p.mag_eps);
+                    tile1[1024 - k] = magnitude<kPower>(X1.x, X1.y, p.mag_eps);
                 }
             });
             if (lane == 0) {  // bin 512 (k1 = 0, k2 = 16) is its own partner
                 const float2 A = a[fft32_pos(16)];
-                float re0, im0, re1 = 0.f;
                 if constexpr (kPair) {
-                    re0 = 2.f * A.x, im0 = 0.f, re1 = 2.f * A.y;
+                    tile2[512] = make_float2(magnitude<kPower>(2.f * A.x, 0.f, p.mag_eps),
+                                             magnitude<kPower>(2.f * A.y, 0.f, p.mag_eps));
                 } else {  // E = 2 Re A, O = 2 Im A, W_2048^512 = -i  ->  X[512] = 2 (Re A - i Im A)
-                    re0 = 2.f * A.x, im0 = -2.f * A.y;
-                }
-                const float m0 = magnitude<kPower>(re0, im0, p.mag_eps);
-                const float m1 = magnitude<kPower>(re1, 0.f, p.mag_eps);
-                if constexpr (kMel) {
-                    if constexpr (kPair) tile2[512] = make_float2(m0, m1);
-                    else tile1[512] = m0;
-                }
-                if constexpr (kSpec != B200MEL_SPEC_NONE) {
-                    const long long o = (b * p.n_freq + 512) * (long long)p.T + t0;
-                    if constexpr (kSpec == B200MEL_SPEC_RE_IM) {
-                        p.out_a[o] = re0, p.out_b[o] = im0;
-                        if (kPair && t.valid1) p.out_a[o + 1] = re1, p.out_b[o + 1] = 0.f;
-                    } else {
-                        p.out_a[o] = m0;
-                        if (kPair && t.valid1) p.out_a[o + 1] = m1;
-                        if constexpr (kSpec == B200MEL_SPEC_MAG_PHASE) {
-                            p.out_b[o] = atan2f(im0, re0);
-                            if (kPair && t.valid1) p.out_b[o + 1] = atan2f(0.f, re1);
-                        }
-                    }
+                    tile1[512] = magnitude<kPower>(2.f * A.x, -2.f * A.y, p.mag_eps);
                 }
             }
-            if constexpr (kMel) {  // zero the padded tail the float4 weight groups may touch
-                if (lane < 7) {
-                    if constexpr (kPair) tile2[513 + lane] = make_float2(0.f, 0.f);
-                    else tile1[1025 + lane] = 0.f;
-                }
+            if (lane < 7) {  // zero the padded tail the float4 weight groups may touch
+                if constexpr (kPair) tile2[513 + lane] = make_float2(0.f, 0.f);
+                else tile1[1025 + lane] = 0.f;
             }
             __syncwarp();
         }
@@ -618,22 +514,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
             // per-item features (data/dataset.py:230-250).
             const int tz0 = t.valid0 ? t0 + 1 : t0;
             const int tz1 = t0 + p.pair_frames - 1;
-            for (int tt = tz0; tt <= tz1 && tt < p.T; ++tt) {
-                if (kMel)
-                    for (int m = lane; m < p.n_mels; m += 32) p.out_mel[(b * p.n_mels + m) * (long long)p.T + tt] = 0.f;
-                if (kSpec != B200MEL_SPEC_NONE)
-                    for (int k = lane; k < p.n_freq; k += 32) {
-                        const long long o = (b * p.n_freq + k) * (long long)p.T + tt;
-                        p.out_a[o] = 0.f;
-                        if (kSpec != B200MEL_SPEC_MAG) p.out_b[o] = 0.f;
-                    }
-            }
-            if (!t.valid0) continue;
+            for (int tt = tz0; tt <= tz1 && tt < p.T; ++tt)
+                for (int m = lane; m < p.n_mels; m += 32) p.out_mel[(b * p.n_mels + m) * (long long)p.T + tt] = 0.f;
         }
-
         PHASE_MARK(8);  // separation + magnitudes
+
         // ---------------------------------------------------------------------- banded mel + log epilogue
-        if constexpr (kMel) {
+        if (t.valid0) {
             float *orow = p.out_mel + b * p.n_mels * (long long)p.T + t0;
             const int4 *ent4 = reinterpret_cast<const int4 *>(s_ent) + lane;
             const float4 *wbase = reinterpret_cast<const float4 *>(s_melw) + lane;
@@ -645,8 +532,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
                 if (r + 1 < p.mel_rounds) e = ent4[(r + 1) * 32];
                 float acc0 = 0.f, acc1 = 0.f;
                 PHASE_MARK(9);  // round setup
-                mel_groups<kPair, (kWarps > 16 ? 4 : 8)>(p.round_groups[r], wbase + p.round_wbase[r], tile_bytes + cur.x * (kPair ? 8 : 4), acc0,
-                                  acc1);
+                mel_groups<kPair, (kWarps > 16 ? 4 : 8)>(p.round_groups[r], wbase + p.round_wbase[r],
+                                                                     tile_bytes + cur.x * (kPair ? 8 : 4), acc0, acc1);
                 PHASE_MARK(10);  // mel FMAs
                 const float y0 = epilogue(acc0, p), y1 = epilogue(acc1, p);
                 PHASE_MARK(11);  // log epilogue
