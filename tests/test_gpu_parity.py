@@ -388,3 +388,27 @@ def test_mfcc_and_patch(torch_cuda):
     assert y.shape == (3, 40, 20)
     assert np.abs(y - ref).max() < 1e-3  # 80-term sums of log values with |.| <= 11.5, each within 1e-4
     assert mf(cuda(torch, x).unsqueeze(1)).shape == (3, 40, 20)
+
+
+def test_stream_ordering_with_pdl(torch_cuda):
+    """The kernel is launched with programmatic dependent launch: its table prologue may overlap the previous
+    kernel, but it must not read `wav` (or overwrite outputs) before that kernel has finished.  A long-running
+    producer writes the input right before each extraction; results must equal the synchronised run."""
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+
+    lm = T.LogMelSpectrogram(**GEO).cuda()
+    base = cuda(torch, mo.synth_clips(64, 22050, 22050, seed=21))
+    ref = lm(base * 0.5 + 0.25)
+    torch.cuda.synchronize()
+    for _ in range(5):
+        x = torch.zeros_like(base)
+        big = torch.empty(64 * 1024 * 1024, device="cuda")
+        big.normal_()                      # keeps the GPU busy in front of the producer
+        x.copy_(base).mul_(0.5).add_(0.25)  # producers of the input, same stream
+        y = lm(x)                          # PDL launch right behind them
+        x.zero_()                          # consumer-after-write on the input must also be ordered
+        assert torch.equal(y, ref)
+    # back-to-back extractions into the same caching-allocator blocks
+    outs = [lm(base * 0.5 + 0.25) for _ in range(8)]
+    assert all(torch.equal(o, ref) for o in outs)
