@@ -356,6 +356,7 @@ def main():
     # ---- with the all-gather of mel frames (north-star's one collective), N > 1 only ---------------------
     gather = None
     if world > 1:
+        # kernel, then the all-gather of its output, on one stream
         def step_gather(i):
             all_gather_mel(module(d_in[i % NBUF]))
 
@@ -363,8 +364,11 @@ def main():
             step_gather(i)
         g_steps = max(3, min(steps, 200))
         ms_g = timed(step_gather, g_steps) / g_steps
+
         gather = {"value": world * HOURS_PER_BATCH / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g,
-                  "bytes_gathered_per_rank": world * B_PER_GPU * N_MELS * T * 4}
+                  "bytes_gathered_per_rank": world * B_PER_GPU * N_MELS * T * 4,
+                  "method": "eager: kernel, then dist.all_gather_into_tensor, one stream (includes the host-side "
+                            "enqueue cost of the collective, which dominates at these message sizes)"}
     sampler.stop()
 
     if rank == 0:
