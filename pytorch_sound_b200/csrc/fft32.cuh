@@ -57,10 +57,15 @@ struct TwConst {
                                       -0.9569403529167175f, -0.9807852506637573f, -0.9951847195625305f, -1.0f};
 };
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex arithmetic on Blackwell's packed FP32x2 pipe: one FADD2 / FMUL2 / FFMA2 (sm_100 SASS) handles the real
+// and imaginary halves of a register pair in ONE issue slot, and ptxas folds half swaps (.LO_HI), per-half sign
+// patterns (.NP / .PN) and scalar broadcasts (.F32) into operand modifiers — so conj(), multiplication by -i and
+// the (c, c) / (-s, s) operands of a complex multiply cost no instructions of their own.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+// a * w = a * (w.x, w.x) + (a.y, a.x) * (-w.y, w.y): FMUL2 + FFMA2
 __device__ __forceinline__ float2 cmul(float2 a, float2 w) {
-    return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+    return __ffma2_rn(a, make_float2(w.x, w.x), __fmul2_rn(make_float2(a.y, a.x), make_float2(-w.y, w.y)));
 }
 // a * (-i)
 __device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }
@@ -75,14 +80,14 @@ __device__ __forceinline__ float2 twiddle32(float2 a) {
         return cmul_mi(a);
     } else if constexpr (J == 16) {
         return make_float2(-a.x, -a.y);
-    } else if constexpr (J == 4) {  // (1 - i)/sqrt2
-        return make_float2((a.x + a.y) * h, (a.y - a.x) * h);
-    } else if constexpr (J == 12) {  // (-1 - i)/sqrt2
-        return make_float2((a.y - a.x) * h, -(a.x + a.y) * h);
+    } else if constexpr (J == 4) {  // (1 - i)/sqrt2:  ((a.x + a.y) h, (a.y - a.x) h)
+        return __fmul2_rn(__fadd2_rn(a, make_float2(a.y, -a.x)), make_float2(h, h));
+    } else if constexpr (J == 12) {  // (-1 - i)/sqrt2: ((a.y - a.x) h, -(a.x + a.y) h)
+        return __fmul2_rn(__fadd2_rn(make_float2(a.y, a.x), make_float2(-a.x, a.y)), make_float2(h, -h));
     } else {
         constexpr float c = TwConst::c32[J];
         constexpr float s = TwConst::s32[J];
-        return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
+        return cmul(a, make_float2(c, s));
     }
 }
 

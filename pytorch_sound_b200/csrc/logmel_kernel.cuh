@@ -146,6 +146,15 @@ __device__ __forceinline__ float epilogue(float x, const KParams &p) {
     return fmaf(y, p.norm_scale, p.norm_bias);
 }
 
+// magnitudes of two complex values at once: {|u|, |v|} (power 1) or {|u|^2, |v|^2} (power 2)
+template <int kPower>
+__device__ __forceinline__ float2 magnitude2(float2 u, float2 v, float eps) {
+    float2 sq = make_float2(fmaf(u.x, u.x, u.y * u.y), fmaf(v.x, v.x, v.y * v.y));
+    if constexpr (kPower == 2) return sq;
+    sq = __fadd2_rn(sq, make_float2(eps, eps));
+    return make_float2(sqrt_approx(sq.x), sqrt_approx(sq.y));
+}
+
 template <int kPower>
 __device__ __forceinline__ float magnitude(float re, float im, float eps) {
     const float sq = fmaf(re, re, im * im);
@@ -205,33 +214,35 @@ __device__ __forceinline__ void issue_stage(const KParams &p, const Task &t, flo
 // once per group.  `w4` points at the lane's first weight group ([group][lane] layout, stride 32 float4).
 template <bool kPair, int G>
 __device__ __forceinline__ void mel_round(const float4 *w4, const void *tile_at_lo, float &acc0, float &acc1) {
-    float b0 = 0.f, b1 = 0.f;
     if constexpr (kPair) {
-        const float4 *mg = reinterpret_cast<const float4 *>(tile_at_lo);  // {|X_t[k]|, |X_t+1[k]|, |X_t[k+1]|, |X_t+1[k+1]|}
+        // {|X_t[k]|, |X_t+1[k]|, |X_t[k+1]|, |X_t+1[k+1]|}: both frames of a bin advance in one FFMA2
+        const float4 *mg = reinterpret_cast<const float4 *>(tile_at_lo);
         float4 w[G], u[G], v[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) w[g] = w4[g * 32], u[g] = mg[2 * g], v[g] = mg[2 * g + 1];
+        float2 a = make_float2(acc0, acc1), b = make_float2(0.f, 0.f);  // two independent accumulation chains
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            acc0 = fmaf(w[g].x, u[g].x, acc0), acc1 = fmaf(w[g].x, u[g].y, acc1);
-            b0 = fmaf(w[g].y, u[g].z, b0), b1 = fmaf(w[g].y, u[g].w, b1);
-            acc0 = fmaf(w[g].z, v[g].x, acc0), acc1 = fmaf(w[g].z, v[g].y, acc1);
-            b0 = fmaf(w[g].w, v[g].z, b0), b1 = fmaf(w[g].w, v[g].w, b1);
+            a = __ffma2_rn(make_float2(u[g].x, u[g].y), make_float2(w[g].x, w[g].x), a);
+            b = __ffma2_rn(make_float2(u[g].z, u[g].w), make_float2(w[g].y, w[g].y), b);
+            a = __ffma2_rn(make_float2(v[g].x, v[g].y), make_float2(w[g].z, w[g].z), a);
+            b = __ffma2_rn(make_float2(v[g].z, v[g].w), make_float2(w[g].w, w[g].w), b);
         }
+        a = __fadd2_rn(a, b);
+        acc0 = a.x, acc1 = a.y;
     } else {
         const float4 *mg = reinterpret_cast<const float4 *>(tile_at_lo);
         float4 w[G], u[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) w[g] = w4[g * 32], u[g] = mg[g];
+        float2 a = make_float2(acc0, 0.f);  // even / odd terms of the single frame in the two halves
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            acc0 = fmaf(w[g].x, u[g].x, acc0);
-            b0 = fmaf(w[g].y, u[g].y, b0);
-            acc0 = fmaf(w[g].z, u[g].z, acc0);
-            b0 = fmaf(w[g].w, u[g].w, b0);
+            a = __ffma2_rn(make_float2(u[g].x, u[g].y), make_float2(w[g].x, w[g].y), a);
+            a = __ffma2_rn(make_float2(u[g].z, u[g].w), make_float2(w[g].z, w[g].w), a);
         }
+        acc0 = a.x + a.y;
     }
-    acc0 += b0, acc1 += b1;
 }
 
 // Runs `groups` (warp-uniform) weight groups as straight-line chunks of 8 / 4 / 2 / 1.
@@ -401,8 +412,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float w = s_win[32 * j + lane];
-                        a[j].x = x0[32 * j] * w;
-                        a[j].y = x1[32 * j] * w;
+                        a[j] = __fmul2_rn(make_float2(x0[32 * j], x1[32 * j]), make_float2(w, w));  // one FMUL2
                     }
                 } else {
 #pragma unroll
@@ -414,11 +424,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
             } else {
                 const float2 *w2 = reinterpret_cast<const float2 *>(s_win);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float2 w = w2[32 * j + lane];
-                    a[j].x = x0[64 * j + lane] * w.x;        // sample 64 j + 2 lane
-                    a[j].y = x0[64 * j + lane + 1] * w.y;    // sample 64 j + 2 lane + 1
-                }
+                for (int j = 0; j < 32; ++j)  // samples 64 j + 2 lane, 64 j + 2 lane + 1
+                    a[j] = __fmul2_rn(make_float2(x0[64 * j + lane], x0[64 * j + lane + 1]), w2[32 * j + lane]);
             }
 
             // -------------------------------------------------------------- 1024-point complex FFT
@@ -478,27 +485,30 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
                 Bv.x = __shfl_sync(0xffffffffu, lane == 0 ? g0.x : g1.x, partner);
                 Bv.y = __shfl_sync(0xffffffffu, lane == 0 ? g0.y : g1.y, partner);
                 const int k = lane + 32 * k2;
-                // E = A + conj(B), O = (A - conj(B)) / i   (the 1/2 is folded into the window)
-                const float2 E = make_float2(A.x + Bv.x, A.y - Bv.y);
-                const float2 O = make_float2(A.y + Bv.y, Bv.x - A.x);
+                // E = A + conj(B), D = A - conj(B) (the 1/2 is folded into the window): frame t is E, frame t+1 is
+                // O = -i D, and |O| = |D|, so the rotation is never formed.  conj() is an operand sign pattern.
+                const float2 Bc = make_float2(Bv.x, -Bv.y);
+                const float2 E = __fadd2_rn(A, Bc);
+                const float2 D = __fadd2_rn(A, make_float2(-Bc.x, -Bc.y));
                 if constexpr (kPair) {
-                    tile2[k] = make_float2(magnitude<kPower>(E.x, E.y, p.mag_eps), magnitude<kPower>(O.x, O.y, p.mag_eps));
+                    tile2[k] = magnitude2<kPower>(E, D, p.mag_eps);
                 } else {
-                    // X[k] = E + W_2048^k O,  X[1024-k] = conj(E - W_2048^k O),  W_2048^k = wl * W_64^{k2}
+                    // X[k] = E + W_2048^k O,  X[1024-k] = conj(E - W_2048^k O),  O = -i D,  W_2048^k = wl * W_64^{k2}
+                    // -> P = D * (-i wl W_64^{k2})
                     constexpr float w64c = TwConst::c64[k2], w64s = TwConst::s64[k2];
-                    const float2 P = cmul(O, cmul(wl, make_float2(w64c, w64s)));
-                    const float2 X0 = cadd(E, P), X1 = csub(E, P);
-                    tile1[k] = magnitude<kPower>(X0.x, X0.y, p.mag_eps);
-                    tile1[1024 - k] = magnitude<kPower>(X1.x, X1.y, p.mag_eps);
+                    const float2 Wk = cmul(wl, make_float2(w64c, w64s));
+                    const float2 P = cmul(D, make_float2(Wk.y, -Wk.x));
+                    const float2 m = magnitude2<kPower>(__fadd2_rn(E, P), __fadd2_rn(E, make_float2(-P.x, -P.y)), p.mag_eps);
+                    tile1[k] = m.x;
+                    tile1[1024 - k] = m.y;
                 }
             });
             if (lane == 0) {  // bin 512 (k1 = 0, k2 = 16) is its own partner
                 const float2 A = a[fft32_pos(16)];
                 if constexpr (kPair) {
-                    tile2[512] = make_float2(magnitude<kPower>(2.f * A.x, 0.f, p.mag_eps),
-                                             magnitude<kPower>(2.f * A.y, 0.f, p.mag_eps));
+                    tile2[512] = magnitude2<kPower>(make_float2(2.f * A.x, 0.f), make_float2(2.f * A.y, 0.f), p.mag_eps);
                 } else {  // E = 2 Re A, O = 2 Im A, W_2048^512 = -i  ->  X[512] = 2 (Re A - i Im A)
-                    tile1[512] = magnitude<kPower>(2.f * A.x, -2.f * A.y, p.mag_eps);
+                    tile1[512] = magnitude2<kPower>(make_float2(2.f * A.x, -2.f * A.y), make_float2(0.f, 0.f), p.mag_eps).x;
                 }
             }
             if (lane < 7) {  // zero the padded tail the float4 weight groups may touch

@@ -130,17 +130,13 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) spec_kernel(const KParams 
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float w = s_win[32 * j + lane];
-                    a[j].x = x0[32 * j] * w;
-                    a[j].y = t.valid1 ? x1[32 * j] * w : 0.f;
+                    a[j] = __fmul2_rn(make_float2(x0[32 * j], t.valid1 ? x1[32 * j] : 0.f), make_float2(w, w));
                 }
             } else {
                 const float2 *w2 = reinterpret_cast<const float2 *>(s_win);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float2 w = w2[32 * j + lane];
-                    a[j].x = x0[64 * j + lane] * w.x;
-                    a[j].y = x0[64 * j + lane + 1] * w.y;
-                }
+                for (int j = 0; j < 32; ++j)
+                    a[j] = __fmul2_rn(make_float2(x0[64 * j + lane], x0[64 * j + lane + 1]), w2[32 * j + lane]);
             }
             fft32(a);
             __syncwarp();
@@ -188,8 +184,10 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) spec_kernel(const KParams 
                 Bv.x = __shfl_sync(0xffffffffu, lane == 0 ? g0.x : g1.x, partner);
                 Bv.y = __shfl_sync(0xffffffffu, lane == 0 ? g0.y : g1.y, partner);
                 const int k = lane + 32 * k2;
-                const float2 E = make_float2(A.x + Bv.x, A.y - Bv.y);
-                const float2 O = make_float2(A.y + Bv.y, Bv.x - A.x);
+                const float2 Bc = make_float2(Bv.x, -Bv.y);                     // conj(B): an operand sign pattern
+                const float2 E = __fadd2_rn(A, Bc);                             // frame t
+                const float2 D = __fadd2_rn(A, make_float2(-Bc.x, -Bc.y));
+                const float2 O = make_float2(D.y, -D.x);                        // frame t+1 = -i (A - conj(B))
                 if constexpr (kPair) {
                     spec_deposit<kSpec>(tile_a, tile_b, k * kRowStride + col, E.x, E.y, p.mag_eps);
                     spec_deposit<kSpec>(tile_a, tile_b, k * kRowStride + col + 1, O.x, O.y, p.mag_eps);
