@@ -320,6 +320,21 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
         if (tid < p.n_fft / 4) t_win = __ldg(reinterpret_cast<const int4 *>(p.window) + tid);
         if (tid < p.mel_rounds * 32) t_ent = __ldg(reinterpret_cast<const int4 *>(p.mel_entries) + tid);
     }
+    // Hint only: pull the first task's span towards L2 while the previous kernel may still be running.  L2 is the
+    // point of coherence, so a producer that writes wav afterwards simply updates the line; the real (TMA) read
+    // happens after griddepcontrol.wait.
+    if (lane == 0 && task < p.n_tasks) {
+        const Task t = decode_task<kPair>(p, cb, cq);
+        if (t.valid0) {
+            const float *row = p.wav + t.b * p.row_stride;
+            const int p_lo = max(t.s_first, 0), p_hi = min(t.s_first + t.span, t.Li);
+            const uintptr_t a16 = reinterpret_cast<uintptr_t>(row + p_lo) & ~(uintptr_t)15;
+            const uintptr_t e16 = (reinterpret_cast<uintptr_t>(row + p_hi) + 15) & ~(uintptr_t)15;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(reinterpret_cast<const void *>(a16))),
+                         "r"((uint32_t)(e16 - a16))
+                         : "memory");
+        }
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     // every warp gets its first task's samples moving before the tables are stored
     if (lane == 0 && task < p.n_tasks) {
@@ -407,7 +422,18 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
             const float *x0 = stage + acquire_stage(t) + lane;
             PHASE_MARK(2);  // wait for the TMA stage
             if constexpr (kPair) {
-                if (t.valid1) {
+                if (t.valid1 && p.hop == 256) {
+                    // hop = 8 * 32: element j of frame t+1 IS element j+8 of frame t in the stage -> 40 distinct
+                    // shared-memory loads per lane for the two frames instead of 64 (the kernel is LSU-bound)
+                    float raw[40];
+#pragma unroll
+                    for (int j = 0; j < 40; ++j) raw[j] = x0[32 * j];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float w = s_win[32 * j + lane];
+                        a[j] = __fmul2_rn(make_float2(raw[j], raw[j + 8]), make_float2(w, w));
+                    }
+                } else if (t.valid1) {
                     const float *x1 = x0 + p.hop;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
