@@ -37,6 +37,7 @@ static const bool g_pdl = [] {  // B200MEL_PDL=0 disables programmatic dependent
     const char *e = getenv("B200MEL_PDL");
     return !(e && e[0] == '0');
 }();
+static const bool g_table_window = getenv("B200MEL_TABLE_WINDOW") != nullptr;  // A/B: read the Hann table instead
 static long long *g_dbg = nullptr;  // device buffer for -DB200MEL_PHASE_TIMING builds (b200mel_debug_set_buffer)
 
 static int fail(int code, const std::string &msg) {
@@ -113,6 +114,7 @@ struct b200mel_plan {
     MelEntry *d_mel_entries = nullptr;
     float *d_mel_w = nullptr;
     int mel_rounds = 0, mel_w_len = 0;
+    int top_groups = 16;  // 32-bin groups the pair kernel separates: 12 when the filterbank ends below bin 384
     int round_groups[kMaxMelRounds] = {0}, round_wbase[kMaxMelRounds] = {0};
     // shared-memory layout
     int off_window = 0, off_entries = 0, off_melw = 0, off_bar = 0, off_regions = 0, region_bytes = 0, stage_bytes = 0;
@@ -147,10 +149,10 @@ static int layout_smem(b200mel_plan *pl) {
     pl->off_entries = pl->off_window + n_fft * 4;
     pl->off_melw = pl->off_entries + pl->mel_rounds * 32 * (int)sizeof(MelEntry);
     pl->off_bar = pl->off_melw + pl->mel_w_len * 4;
-    pl->off_regions = (pl->off_bar + kMaxWarps * 8 + 127) & ~127;
+    pl->off_regions = (pl->off_bar + (kMaxWarps + 1) * 8 + 127) & ~127;  // per-warp mbarriers + the table mbarrier
     int n_warps = (kMaxSmem - pl->off_regions) / pl->region_bytes;
     int cap = kDefaultWarps;
-    if (const char *env = getenv("B200MEL_WARPS")) cap = atoi(env);  // tuning knob: 16, 20 or 24
+    if (const char *env = getenv("B200MEL_WARPS")) cap = atoi(env);  // debugging knob: fewer warps per CTA
     if (cap < 1) cap = 1;
     if (cap > kMaxWarps) cap = kMaxWarps;
     if (n_warps > cap) n_warps = cap;
@@ -183,8 +185,9 @@ static int layout_smem(b200mel_plan *pl) {
 static int upload_filterbank(b200mel_plan *pl, const float *W, int n_mels, int F) {
     struct Row { int m, lo, cnt; };
     const int align = pl->pair ? 2 : 4;  // tile elements per 16 bytes (float2 pairs vs float)
-    const int tile_len = pl->pair ? kPairTileLen : kSplitTileLen;
+    int tile_len = pl->pair ? kPairTileLen : kSplitTileLen;
     std::vector<Row> rows(n_mels);
+    int top = 0;  // one past the highest bin any row touches
     for (int m = 0; m < n_mels; ++m) {
         int first = -1, last = -1;
         for (int k = 0; k < F; ++k)
@@ -193,6 +196,15 @@ static int upload_filterbank(b200mel_plan *pl, const float *W, int n_mels, int F
                 last = k;
             }
         rows[m] = {m, first < 0 ? 0 : first, first < 0 ? 0 : last - first + 1};
+        top = std::max(top, last + 1);
+    }
+    // Pair mode with a filterbank that ends below bin 384 (e.g. fmax = 8000 Hz at 22050 Hz): the kernel variant
+    // that separates only the first 12 groups of 32 bins is used, and every read window is kept below bin 384.
+    pl->top_groups = 16;
+    if (pl->pair && top <= 384 && !getenv("B200MEL_NO_PRUNE")) {
+        bool fits = true;
+        for (int m = 0; m < n_mels; ++m) fits = fits && (rows[m].cnt + 8 <= 384);
+        if (fits) pl->top_groups = 12, tile_len = 384;
     }
     auto need = [&](const Row &r) { return (r.cnt + r.lo % align + 3) / 4; };  // groups incl. alignment lead-in
     std::stable_sort(rows.begin(), rows.end(), [&](const Row &x, const Row &y) { return need(x) > need(y); });
@@ -280,19 +292,15 @@ static int upload_filterbank(b200mel_plan *pl, const float *W, int n_mels, int F
 }
 
 typedef void (*kernel_fn)(const KParams);
-// The mel kernels exist in 16 / 20 / 24-warp builds (128 / 96 / 80 registers per thread); the spectrum-output
-// operators use the 8-warp cooperative kernel of spec_kernel.cuh.
-template <int kWarps>
+// Mel kernels: {pair, split} x {magnitude, power} x {all bins, bins < 384 (pair only)}, 16 warps per CTA; the
+// spectrum-output operators use the 8-warp cooperative kernel of spec_kernel.cuh.
+template <int kTop>
 static kernel_fn pick_mel_kernel(bool pair, int power) {
-    if (pair) return power == 2 ? logmel_kernel<true, 2, kWarps> : logmel_kernel<true, 1, kWarps>;
-    return power == 2 ? logmel_kernel<false, 2, kWarps> : logmel_kernel<false, 1, kWarps>;
+    if (pair) return power == 2 ? logmel_kernel<true, 2, kTop> : logmel_kernel<true, 1, kTop>;
+    return power == 2 ? logmel_kernel<false, 2, 16> : logmel_kernel<false, 1, 16>;
 }
-static kernel_fn pick_kernel(bool pair, int spec, bool mel, int power, int warps) {
-    if (mel) {
-        if (warps > 20) return pick_mel_kernel<24>(pair, power);
-        if (warps > 16) return pick_mel_kernel<20>(pair, power);
-        return pick_mel_kernel<16>(pair, power);
-    }
+static kernel_fn pick_kernel(bool pair, int spec, bool mel, int power, int top_groups) {
+    if (mel) return top_groups == 12 ? pick_mel_kernel<12>(pair, power) : pick_mel_kernel<16>(pair, power);
     switch (spec) {
         case B200MEL_SPEC_MAG_PHASE: return pair ? spec_kernel<true, 1> : spec_kernel<false, 1>;
         case B200MEL_SPEC_RE_IM: return pair ? spec_kernel<true, 2> : spec_kernel<false, 2>;
@@ -383,10 +391,10 @@ int b200mel_plan_create(const b200mel_config *cfg, b200mel_plan **out) {
     for (auto &w : win) w *= 0.5f;  // exact; the separation pass omits its 1/2
     std::vector<float2> tw(32 * 32), twp(32);
     const double two_pi = 6.283185307179586476925286766559;
-    for (int k1 = 0; k1 < 32; ++k1)
+    for (int j = 0; j < 32; ++j)  // [j / 2][lane][j & 1]: one 128-bit load fetches the twiddles of slots j, j + 1
         for (int l = 0; l < 32; ++l) {
-            double ang = two_pi * (double)(k1 * l) / 1024.0;
-            tw[k1 * 32 + l] = make_float2((float)cos(ang), (float)-sin(ang));
+            double ang = two_pi * (double)(j * l) / 1024.0;
+            tw[((j >> 1) * 32 + l) * 2 + (j & 1)] = make_float2((float)cos(ang), (float)-sin(ang));
         }
     for (int l = 0; l < 32; ++l) {
         double ang = two_pi * l / 2048.0;
@@ -412,8 +420,8 @@ int b200mel_plan_create(const b200mel_config *cfg, b200mel_plan **out) {
         for (int spec = 0; spec <= 3 && e == cudaSuccess; ++spec)
             for (int power = 1; power <= 2 && e == cudaSuccess; ++power) {
                 if (spec != 0 && power == 2) continue;
-                for (int warps = 16; warps <= (spec == 0 ? 24 : 16) && e == cudaSuccess; warps += 4)
-                    e = cudaFuncSetAttribute(pick_kernel(pl->pair, spec, spec == 0, power, warps),
+                for (int top = 12; top <= (spec == 0 ? 16 : 12) && e == cudaSuccess; top += 4)
+                    e = cudaFuncSetAttribute(pick_kernel(pl->pair, spec, spec == 0, power, top),
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
             }
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute (is the library built for this GPU?)"); break; }
@@ -456,6 +464,7 @@ int b200mel_forward(const b200mel_plan *pl, const float *wav, int64_t B, int64_t
                     float *out_a, float *out_b, void *stream) {
     if (!pl) return fail(B200MEL_EINVAL, "forward: null plan");
     if (B < 0 || L < 0) return fail(B200MEL_EINVAL, "forward: negative shape");
+    if (B > 0x7fffffff) return fail(B200MEL_EINVAL, "forward: more than 2^31 - 1 clips");
     if (B == 0) return B200MEL_OK;
     if (!wav) return fail(B200MEL_EINVAL, "forward: null wav");
     if (row_stride < L) return fail(B200MEL_EINVAL, "forward: row_stride < L");
@@ -492,6 +501,7 @@ int b200mel_forward(const b200mel_plan *pl, const float *wav, int64_t B, int64_t
     p.pad = pl->pad;
     p.n_fft = pl->cfg.n_fft;
     p.pair_frames = pl->pair_frames;
+    p.hann_full = (pl->pair && pl->cfg.win_length == pl->cfg.n_fft && !g_table_window) ? 1 : 0;
     p.window = pl->d_window;
     p.tw = pl->d_tw;
     p.tw_post = pl->d_tw_post;
@@ -557,7 +567,7 @@ int b200mel_forward(const b200mel_plan *pl, const float *wav, int64_t B, int64_t
     if (out_mel) {
         cfg.gridDim = dim3((unsigned)n_cta);
         cfg.blockDim = dim3(pl->n_warps * 32);
-        le = cudaLaunchKernelEx(&cfg, pick_kernel(pl->pair, 0, true, pl->cfg.power, pl->n_warps), p);
+        le = cudaLaunchKernelEx(&cfg, pick_kernel(pl->pair, 0, true, pl->cfg.power, pl->top_groups), p);
         g_launches.fetch_add(1);
     }
     if (spec_kind && le == cudaSuccess) {

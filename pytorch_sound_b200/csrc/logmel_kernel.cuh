@@ -41,9 +41,12 @@
 
 namespace b200mel {
 
-constexpr int kMaxWarps = 24;  // upper bound over all kernel variants (mbarrier array size)
-constexpr int kBufStride = 33;                           // float2 per transposed row (+1 pad)
-constexpr int kXposeBytes = 32 * kBufStride * 8;          // 8448
+constexpr int kMaxWarps = 16;   // warps per CTA of the mel kernel (register budget 65536 / (32 * 16) = 128)
+// float2 per transposed row: 272 B = 17 x 16 B, so a lane reads ITS row with 128-bit loads (two values per LDS)
+// and the 8 lanes of a quarter warp hit 8 different 16-byte bank groups (17 l mod 8 = l); the write side stores
+// 32 consecutive float2 per row, conflict-free for any stride.
+constexpr int kBufStride = 34;
+constexpr int kXposeBytes = 32 * kBufStride * 8;          // 8704
 constexpr int kTileBytes = 4160;                          // magnitude tile
 constexpr int kStageOff = 4224;                           // stage offset inside the warp region (128B aligned)
 constexpr int kPairTileLen = 520;                         // float2 entries (513 used, tail zeroed)
@@ -66,9 +69,10 @@ struct KParams {
     const int *lengths;
     int T, hop, pad, n_fft;
     int pair_frames;  // frames per task: 2 (pair mode) or 1 (split mode, or pair mode with hop > n_fft)
+    int hann_full;    // 1: win_length == n_fft, the kernel may generate the periodic Hann instead of reading the table
     // global copies of the CTA tables
     const float *window;    // [n_fft], periodic Hann centre-padded, pre-scaled by 0.5
-    const float2 *tw;       // [32][32]  tw[k1*32 + lane] = exp(-2 pi i k1 lane / 1024)
+    const float2 *tw;       // [16][32][2]  tw[((j >> 1) * 32 + lane) * 2 + (j & 1)] = exp(-2 pi i j lane / 1024)
     const float2 *tw_post;  // [32]      exp(-2 pi i lane / 2048)            (split mode)
     const MelEntry *mel_entries;  // [rounds][32]
     const float *mel_w;           // [mel_w_len]
@@ -271,10 +275,49 @@ __device__ __forceinline__ void mel_groups(int groups, const float4 *w4, const u
     }
 }
 
-// kPower: 1 magnitude, 2 power.  kWarps: warps per CTA the variant is compiled for (register budget =
-// 65536 / (32 kWarps)).
-template <bool kPair, int kPower, int kWarps>
-__global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p) {
+// Transposed read-back between the two radix-32 passes (lane = k1, slot = n2) with the inter-pass twiddle
+// W_1024^{n2 k1} applied on the read side.  Both the lane's row of the transpose buffer and the twiddle table
+// ([n2 / 2][lane][2]) are read with 128-bit loads — two complex values per LDS — and each batch issues all its
+// loads back to back before the multiplies (deep memory-level parallelism; the a[] registers are free here).
+template <int kB>
+__device__ __forceinline__ void xpose_read_twiddle(float2 *a, const float2 *buf, const float2 *s_tw, int lane) {
+    const float4 *row = reinterpret_cast<const float4 *>(buf + lane * kBufStride);
+    const float4 *tw4 = reinterpret_cast<const float4 *>(s_tw) + lane;
+    static_for<0, 32 / kB>([&](auto h_) {
+        constexpr int h = decltype(h_)::value;
+        float4 v[kB / 2], t[kB / 2];
+#pragma unroll
+        for (int i = 0; i < kB / 2; ++i) v[i] = row[h * (kB / 2) + i];
+#pragma unroll
+        for (int i = 0; i < kB / 2; ++i)
+#ifdef B200MEL_X_NOTW  // upper-bound probe: no twiddle-table loads (wrong results)
+            t[i] = make_float4(0.6f, 0.8f, 0.8f, -0.6f);
+#else
+            t[i] = tw4[(h * (kB / 2) + i) * 32];
+#endif
+#pragma unroll
+        for (int i = 0; i < kB / 2; ++i) {
+            const int j = h * kB + 2 * i;
+            a[j] = j > 0 ? cmul(make_float2(v[i].x, v[i].y), make_float2(t[i].x, t[i].y)) : make_float2(v[i].x, v[i].y);
+            a[j + 1] = cmul(make_float2(v[i].z, v[i].w), make_float2(t[i].z, t[i].w));
+        }
+    });
+}
+
+// What the consume side of a task needs to know, computed ONCE when the task's samples are requested and carried
+// in registers until the task is processed (the prefetch runs one task ahead).
+struct Desc {
+    int b, t0;        // clip, first frame
+    int delta;        // stage shift: sample s of the span sits at stage[s - s_first + delta]
+    int Li;           // clip length (p.L unless `lengths`)
+    unsigned flags;   // 1: frame t0 exists, 2: frame t0+1 exists (pair mode), 4: span leaves [0, Li) (reflect patch)
+};
+
+// kPower: 1 magnitude, 2 power.  kTop: 32-bin groups of the spectrum that are separated in pair mode — 16 = all
+// 513 bins, 12 = bins 0..383 only (plans whose filterbank ends below bin 384, e.g. fmax 8000 Hz at 22050 Hz; the
+// unused FFT outputs are dead code for the compiler).  16 warps per CTA (128 registers per thread).
+template <bool kPair, int kPower, int kTop>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_warps = blockDim.x >> 5;
@@ -296,82 +339,108 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
     float2 *tile2 = reinterpret_cast<float2 *>(region);        // pair-mode magnitude tile
     float *tile1 = reinterpret_cast<float *>(region);          // split-mode magnitude tile
     float *stage = reinterpret_cast<float *>(region + kStageOff);
+    const uint32_t stage_s = smem_u32(stage);
     const uint32_t bar = smem_u32(s_bar + warp);
     uint32_t parity = 0;
 
-    // task = cb * tasks_per_clip + cq, advanced by the grid-wide warp stride without any division
+    // task = cb * tasks_per_clip + cq, advanced by the grid-wide warp stride without any division.  The warps of
+    // one CTA take tasks gridDim.x apart (task = warp * gridDim.x + blockIdx.x), so the partial last round of a
+    // launch spreads over ALL SMs instead of filling the first CTAs' 16 warps and leaving the others idle.
     const long long stride = (long long)gridDim.x * n_warps;
-    long long task = (long long)blockIdx.x * n_warps + warp;
-    long long cb = task / p.tasks_per_clip;
-    int cq = (int)(task - cb * p.tasks_per_clip);
+    long long task = (long long)warp * gridDim.x + blockIdx.x;
+    int cb = (int)(task / p.tasks_per_clip);
+    int cq = (int)(task - (long long)cb * p.tasks_per_clip);
+
+    // Locate a task and (one elected lane) request its samples: arm the warp's mbarrier and issue ONE bulk copy of
+    // the in-range part of the span, widened to 16-byte boundaries on both sides (the extra <= 3 floats per side
+    // are never read as samples: interior tasks ignore them, edge tasks overwrite the halo after the copy landed).
+    // Everything is computed uniformly by all lanes in straight-line code, so the scheduler can sink it into the
+    // shadow of the surrounding FFT arithmetic; only the three PTX instructions at the end are predicated.
+    auto request = [&](int b, int q) -> Desc {
+        Desc d;
+        d.b = b;
+        int Li = p.L, Ti = p.T;
+        if (p.lengths) {
+            Li = min(__ldg(p.lengths + b), p.L);
+            Ti = min(frames_of(Li, p.n_fft, p.hop, p.pad), p.T);
+        }
+        d.Li = Li;
+        d.t0 = q * p.pair_frames;
+        const bool v0 = d.t0 < Ti, v1 = kPair && p.pair_frames == 2 && d.t0 + 1 < Ti;
+        const int s_first = d.t0 * p.hop - p.pad;
+        const int span = p.n_fft + (v1 ? p.hop : 0);
+        const int p_lo = max(s_first, 0), p_hi = min(s_first + span, Li);
+        const uintptr_t src = reinterpret_cast<uintptr_t>(p.wav + (long long)b * p.row_stride + p_lo);
+        const int mis = (int)(src >> 2) & 3;   // floats by which the first in-range sample misses a 16-byte boundary
+        const int off = p_lo - s_first;        // its position in the span
+        d.delta = (mis - off) & 3;             // shift that makes stage and global address 16-byte congruent
+        d.flags = (v0 ? 1u : 0u) | (v1 ? 2u : 0u) | ((s_first < 0 || s_first + span > Li) ? 4u : 0u);
+        if (v0 && lane == 0) {
+            const uint32_t bytes = (uint32_t)(((p_hi - p_lo + mis) * 4 + 15) & ~15);
+            fence_proxy_async();
+            mbar_arrive_expect_tx(bar, bytes);
+            tma_load_1d(stage_s + (uint32_t)((off + d.delta - mis) * 4), reinterpret_cast<const void *>(src - 4 * mis), bytes, bar);
+        }
+        return d;
+    };
 
     // Prologue, ordered for programmatic dependent launch (PDL): everything that does not touch caller memory —
-    // mbarrier init and the loads of the plan-owned tables — runs BEFORE griddepcontrol.wait, i.e. it overlaps the
-    // tail of whatever kernel precedes this one in the stream.  Caller memory (wav, outputs) is only touched after
-    // the wait; griddepcontrol.launch_dependents then lets the next launch start its own prologue the same way.
-    if (lane == 0) {
-        mbar_init(bar, 1);
+    // mbarrier init and the fetch of the plan-owned tables — is started BEFORE griddepcontrol.wait, i.e. it overlaps
+    // the tail of whatever kernel precedes this one in the stream.  The tables come in as four bulk copies (TMA)
+    // signalled on one mbarrier, so no thread carries them through registers and their L2 latency runs concurrently
+    // with the first sample fetch.  Caller memory (wav, outputs) is only touched after the wait;
+    // griddepcontrol.launch_dependents then lets the next launch start its own prologue the same way.
+    const uint32_t tbar = smem_u32(s_bar + kMaxWarps);
+    if (lane == 0) mbar_init(bar, 1);
+    if (threadIdx.x == 0) {
+        mbar_init(tbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    int4 t_tw = make_int4(0, 0, 0, 0), t_win = t_tw, t_ent = t_tw;
-    const int tid = threadIdx.x;
-    if (blockDim.x >= 512) {
-        t_tw = __ldg(reinterpret_cast<const int4 *>(p.tw) + tid);
-        if (tid < p.n_fft / 4) t_win = __ldg(reinterpret_cast<const int4 *>(p.window) + tid);
-        if (tid < p.mel_rounds * 32) t_ent = __ldg(reinterpret_cast<const int4 *>(p.mel_entries) + tid);
+        const uint32_t b_tw = 32 * 32 * 8, b_win = (uint32_t)p.n_fft * 4u;
+        const uint32_t b_ent = (uint32_t)p.mel_rounds * 32u * (uint32_t)sizeof(MelEntry), b_w = (uint32_t)p.mel_w_len * 4u;
+        mbar_arrive_expect_tx(tbar, b_tw + b_win + b_ent + b_w);
+        tma_load_1d(smem_u32(s_tw), p.tw, b_tw, tbar);
+        tma_load_1d(smem_u32(s_win), p.window, b_win, tbar);
+        tma_load_1d(smem_u32(smem_raw + p.off_entries), p.mel_entries, b_ent, tbar);
+        tma_load_1d(smem_u32(smem_raw + p.off_melw), p.mel_w, b_w, tbar);
+    } else if (lane == 0) {
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // Hint only: pull the first task's span towards L2 while the previous kernel may still be running.  L2 is the
     // point of coherence, so a producer that writes wav afterwards simply updates the line; the real (TMA) read
     // happens after griddepcontrol.wait.
     if (lane == 0 && task < p.n_tasks) {
-        const Task t = decode_task<kPair>(p, cb, cq);
-        if (t.valid0) {
-            const float *row = p.wav + t.b * p.row_stride;
-            const int p_lo = max(t.s_first, 0), p_hi = min(t.s_first + t.span, t.Li);
-            const uintptr_t a16 = reinterpret_cast<uintptr_t>(row + p_lo) & ~(uintptr_t)15;
-            const uintptr_t e16 = (reinterpret_cast<uintptr_t>(row + p_hi) + 15) & ~(uintptr_t)15;
+        const int s0 = max(cq * p.pair_frames * p.hop - p.pad, 0);
+        const int s1 = min(s0 + p.n_fft + p.hop, p.L);
+        const float *row = p.wav + (long long)cb * p.row_stride;
+        const uintptr_t a16 = reinterpret_cast<uintptr_t>(row + s0) & ~(uintptr_t)15;
+        const uintptr_t e16 = reinterpret_cast<uintptr_t>(row + s1) & ~(uintptr_t)15;
+        if (e16 > a16)
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(reinterpret_cast<const void *>(a16))),
                          "r"((uint32_t)(e16 - a16))
                          : "memory");
-        }
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    // every warp gets its first task's samples moving before the tables are stored
-    if (lane == 0 && task < p.n_tasks) {
-        const Task t = decode_task<kPair>(p, cb, cq);
-        if (t.valid0) issue_stage<kPair>(p, t, stage, bar);
-    }
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // every warp gets its first task's samples moving (its own mbarrier, initialised by its own lane 0)
+    Desc cur;
+    cur.b = cur.t0 = cur.delta = cur.Li = 0;
+    cur.flags = 0;
     __syncwarp();
-    {
-        const int4 *g;
-        int4 *s;
-        if (blockDim.x >= 512) {
-            reinterpret_cast<int4 *>(s_tw)[tid] = t_tw;
-            if (tid < p.n_fft / 4) reinterpret_cast<int4 *>(s_win)[tid] = t_win;
-            if (tid < p.mel_rounds * 32) reinterpret_cast<int4 *>(smem_raw + p.off_entries)[tid] = t_ent;
-            g = reinterpret_cast<const int4 *>(p.window);
-            s = reinterpret_cast<int4 *>(s_win);
-            for (int i = tid + 512; i < p.n_fft / 4; i += blockDim.x) s[i] = __ldg(g + i);  // n_fft > 2048 only
-        } else {
-            g = reinterpret_cast<const int4 *>(p.tw);
-            s = reinterpret_cast<int4 *>(s_tw);
-            for (int i = tid; i < 32 * 32 * 8 / 16; i += blockDim.x) s[i] = __ldg(g + i);
-            g = reinterpret_cast<const int4 *>(p.window);
-            s = reinterpret_cast<int4 *>(s_win);
-            for (int i = tid; i < p.n_fft / 4; i += blockDim.x) s[i] = __ldg(g + i);
-            g = reinterpret_cast<const int4 *>(p.mel_entries);
-            s = reinterpret_cast<int4 *>(smem_raw + p.off_entries);
-            for (int i = tid; i < p.mel_rounds * 32; i += blockDim.x) s[i] = __ldg(g + i);
-        }
-        g = reinterpret_cast<const int4 *>(p.mel_w);
-        s = reinterpret_cast<int4 *>(smem_raw + p.off_melw);
-        for (int i = tid; i < p.mel_w_len / 4; i += blockDim.x) s[i] = __ldg(g + i);
-    }
-    __syncthreads();  // the only block-wide barrier; warps are independent from here on
+    if (task < p.n_tasks) cur = request(cb, cq);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    __syncthreads();      // the only block-wide barrier: the table mbarrier is initialised for everyone
+    mbar_wait(tbar, 0);   // tables have landed (async-proxy writes are visible to the waiting threads)
 
     float2 wl = make_float2(1.f, 0.f);
     if (!kPair) wl = __ldg(p.tw_post + lane);
+    // Full-length periodic Hann (win_length == n_fft) is generated in registers instead of read from the table:
+    // 0.5 w[32 j + lane] = 0.25 - 0.25 cos(2 pi j / 32 + phi), phi = 2 pi lane / 1024 — the angle-addition form
+    // with the compile-time cos/sin of 2 pi j / 32 and the lane's own (0.25 cos phi, 0.25 sin phi).
+    float2 hann_cs = make_float2(0.f, 0.f);
+    if (kPair && p.hann_full) {
+        float sn, cs;
+        sincospif((float)lane * (1.0f / 512.0f), &sn, &cs);
+        hann_cs = make_float2(0.25f * cs, 0.25f * sn);
+    }
 
 #ifdef B200MEL_PHASE_TIMING
     unsigned phase_acc_[14];
@@ -389,51 +458,67 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
     }
 #endif
 
-    // Wait for a task's staged samples and patch its reflected halo (edge tasks only: the out-of-range part of the
-    // span is overwritten after the bulk copy has landed).  Returns the stage shift delta.
-    auto acquire_stage = [&](const Task &tk) -> int {
-        const float *row = p.wav + tk.b * p.row_stride;
-        const int delta = stage_delta(row, tk);
-        mbar_wait(bar, parity);
-        parity ^= 1;
-        if (tk.s_first < 0 || tk.s_first + tk.span > tk.Li) {
-            for (int i = lane; i < tk.span; i += 32) {
-                const int s = tk.s_first + i;
-                if (s < 0 || s >= tk.Li) stage[i + delta] = __ldg(row + reflect_index(s, tk.Li));
-            }
-            __syncwarp();
+    // Reflected halo of an edge task (<= 4 of 44 tasks per 1-s clip): the out-of-range part of the span is filled
+    // after the bulk copy has landed.  The reflected samples are almost always inside the staged in-range part, so
+    // they are copied within shared memory; only a reflection that leaves the span falls back to global memory.
+    auto patch_halo = [&](const Desc &d) {
+        const int s_first = d.t0 * p.hop - p.pad;
+        const int span = p.n_fft + ((d.flags & 2u) ? p.hop : 0);
+        const int p_lo = max(s_first, 0), p_hi = min(s_first + span, d.Li);
+        const float *row = p.wav + (long long)d.b * p.row_stride;
+        float *st = stage + d.delta - s_first;  // st[s] = sample at padded-coordinate position s
+        for (int s = s_first + lane; s < 0; s += 32) {
+            const int r = reflect_index(s, d.Li);
+            st[s] = (r >= p_lo && r < p_hi) ? st[r] : __ldg(row + r);
         }
-        return delta;
+        for (int s = d.Li + lane; s < s_first + span; s += 32) {
+            const int r = reflect_index(s, d.Li);
+            st[s] = (r >= p_lo && r < p_hi) ? st[r] : __ldg(row + r);
+        }
+        __syncwarp();
     };
 
     for (; task < p.n_tasks; task += stride) {
-        const Task t = decode_task<kPair>(p, cb, cq);
+        const Desc d = cur;
         // next task of this warp
         cb += p.stride_b;
         cq += p.stride_q;
         if (cq >= p.tasks_per_clip) cq -= p.tasks_per_clip, ++cb;
-        const long long b = t.b;
-        const int t0 = t.t0;
+        const bool valid0 = d.flags & 1u, valid1 = d.flags & 2u;
         float2 a[32];
 
-        if (t.valid0) {
+        if (valid0) {
             PHASE_MARK(1);  // decode
             // -------------------------------------------------------------- stage -> registers, windowed
-            const float *x0 = stage + acquire_stage(t) + lane;
+            mbar_wait(bar, parity);
+            parity ^= 1;
+            if (d.flags & 4u) patch_halo(d);
+            const float *x0 = stage + d.delta + lane;
             PHASE_MARK(2);  // wait for the TMA stage
             if constexpr (kPair) {
-                if (t.valid1 && p.hop == 256) {
+                if (valid1 && p.hop == 256) {
                     // hop = 8 * 32: element j of frame t+1 IS element j+8 of frame t in the stage -> 40 distinct
                     // shared-memory loads per lane for the two frames instead of 64 (the kernel is LSU-bound)
                     float raw[40];
 #pragma unroll
                     for (int j = 0; j < 40; ++j) raw[j] = x0[32 * j];
+                    if (p.hann_full) {
+                        static_for<0, 16>([&](auto j_) {
+                            constexpr int j = decltype(j_)::value;
+                            // t = 0.25 cos(theta_j + phi); TwConst::s32 holds -sin
+                            const float t = fmaf(TwConst::s32[j], hann_cs.y, TwConst::c32[j] * hann_cs.x);
+                            const float w0 = 0.25f - t, w1 = 0.25f + t;  // slots j and j + 16 (theta + pi)
+                            a[j] = __fmul2_rn(make_float2(raw[j], raw[j + 8]), make_float2(w0, w0));
+                            a[j + 16] = __fmul2_rn(make_float2(raw[j + 16], raw[j + 24]), make_float2(w1, w1));
+                        });
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float w = s_win[32 * j + lane];
-                        a[j] = __fmul2_rn(make_float2(raw[j], raw[j + 8]), make_float2(w, w));
+                        for (int j = 0; j < 32; ++j) {
+                            const float w = s_win[32 * j + lane];
+                            a[j] = __fmul2_rn(make_float2(raw[j], raw[j + 8]), make_float2(w, w));
+                        }
                     }
-                } else if (t.valid1) {
+                } else if (valid1) {
                     const float *x1 = x0 + p.hop;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -464,43 +549,24 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
                 buf[k1 * kBufStride + lane] = a[fft32_pos(k1)];
             });
             __syncwarp();
-            // read back transposed (lane = k1, slot = n2) and apply the inter-pass twiddle W_1024^{n2 k1} on the
-            // read side: the a[] registers are free here, so each batch issues its loads back to back (deep
-            // memory-level parallelism) instead of serialising load -> multiply -> store per element.
-            {
-                constexpr int kB = kWarps > 16 ? 8 : 16;  // loads in flight per batch (register budget of the variant)
-                static_for<0, 32 / kB>([&](auto h_) {
-                    constexpr int h = decltype(h_)::value;
-                    float2 tw[kB];
-#pragma unroll
-                    for (int i = 0; i < kB; ++i) a[h * kB + i] = buf[lane * kBufStride + h * kB + i];
-#pragma unroll
-                    for (int i = 0; i < kB; ++i) tw[i] = s_tw[(h * kB + i) * 32 + lane];
-#pragma unroll
-                    for (int i = 0; i < kB; ++i)
-                        if (h * kB + i > 0) a[h * kB + i] = cmul(a[h * kB + i], tw[i]);
-                });
-            }
+            xpose_read_twiddle<16>(a, buf, s_tw, lane);
             __syncwarp();  // transpose buffer is dead: magnitude tile and next stage may reuse it
             PHASE_MARK(5);  // transpose + twiddle
         }
 
-        // ------------------------------------------------------------------ prefetch the next task's samples
-        Task nxt;
-        nxt.valid0 = false;
-        if (task + stride < p.n_tasks) {
-            nxt = decode_task<kPair>(p, cb, cq);
-            if (nxt.valid0 && lane == 0) issue_stage<kPair>(p, nxt, stage, bar);
-        }
+        // ------------------------------------------------------------------ request the next task's samples
+        cur.flags = 0;
+        if (task + stride < p.n_tasks) cur = request(cb, cq);
 
-        if (t.valid0) {
+        if (valid0) {
             PHASE_MARK(6);  // prefetch issue
             fft32(a);  // pass 2: lane = k1, FFT over n2 -> Z[k1 + 32 k2] at a[pos(k2)]
             PHASE_MARK(7);  // pass 2
 
             // -------------------------------------------------------------- real-input separation + magnitudes
             const int partner = (32 - lane) & 31;
-            static_for<0, 16>([&](auto k2_) {
+            constexpr int kGroups = kPair ? kTop : 16;
+            static_for<0, kGroups>([&](auto k2_) {
                 constexpr int k2 = decltype(k2_)::value;
                 const float2 A = a[fft32_pos(k2)];
                 // value my reader needs: lane 0 is read by itself and wants Z[32*((32-k2)&31)];
@@ -529,60 +595,73 @@ __global__ void __launch_bounds__(kWarps * 32, 1) logmel_kernel(const KParams p)
                     tile1[1024 - k] = m.y;
                 }
             });
-            if (lane == 0) {  // bin 512 (k1 = 0, k2 = 16) is its own partner
-                const float2 A = a[fft32_pos(16)];
-                if constexpr (kPair) {
-                    tile2[512] = magnitude2<kPower>(make_float2(2.f * A.x, 0.f), make_float2(2.f * A.y, 0.f), p.mag_eps);
-                } else {  // E = 2 Re A, O = 2 Im A, W_2048^512 = -i  ->  X[512] = 2 (Re A - i Im A)
-                    tile1[512] = magnitude2<kPower>(make_float2(2.f * A.x, -2.f * A.y), make_float2(0.f, 0.f), p.mag_eps).x;
+            if constexpr (kGroups == 16) {
+                if (lane == 0) {  // bin 512 (k1 = 0, k2 = 16) is its own partner
+                    const float2 A = a[fft32_pos(16)];
+                    if constexpr (kPair) {
+                        tile2[512] = magnitude2<kPower>(make_float2(2.f * A.x, 0.f), make_float2(2.f * A.y, 0.f), p.mag_eps);
+                    } else {  // E = 2 Re A, O = 2 Im A, W_2048^512 = -i  ->  X[512] = 2 (Re A - i Im A)
+                        tile1[512] = magnitude2<kPower>(make_float2(2.f * A.x, -2.f * A.y), make_float2(0.f, 0.f), p.mag_eps).x;
+                    }
                 }
-            }
-            if (lane < 7) {  // zero the padded tail the float4 weight groups may touch
-                if constexpr (kPair) tile2[513 + lane] = make_float2(0.f, 0.f);
-                else tile1[1025 + lane] = 0.f;
-            }
+                if (lane < 7) {  // zero the padded tail the float4 weight groups may touch
+                    if constexpr (kPair) tile2[513 + lane] = make_float2(0.f, 0.f);
+                    else tile1[1025 + lane] = 0.f;
+                }
+            }  // kTop < 16: the plan keeps every read window below bin 32 kTop, all of which were just written
             __syncwarp();
         }
 
         // ---------------------------------------------------------------------- frames past the clip's end
-        if (!t.valid0 || (kPair && p.pair_frames == 2 && !t.valid1)) {
+        if (!valid0 || (kPair && p.pair_frames == 2 && !valid1)) {
             // only with `lengths` (or the odd last frame of a pair): zero-fill, as pad_collate_fn zero-pads
             // per-item features (data/dataset.py:230-250).
-            const int tz0 = t.valid0 ? t0 + 1 : t0;
-            const int tz1 = t0 + p.pair_frames - 1;
+            const int tz0 = valid0 ? d.t0 + 1 : d.t0;
+            const int tz1 = d.t0 + p.pair_frames - 1;
             for (int tt = tz0; tt <= tz1 && tt < p.T; ++tt)
-                for (int m = lane; m < p.n_mels; m += 32) p.out_mel[(b * p.n_mels + m) * (long long)p.T + tt] = 0.f;
+                for (int m = lane; m < p.n_mels; m += 32) p.out_mel[((long long)d.b * p.n_mels + m) * (long long)p.T + tt] = 0.f;
         }
         PHASE_MARK(8);  // separation + magnitudes
 
         // ---------------------------------------------------------------------- banded mel + log epilogue
-        if (t.valid0) {
-            float *orow = p.out_mel + b * p.n_mels * (long long)p.T + t0;
+#ifdef B200MEL_X_NOMEL  // upper-bound probe (tools/variant_bench.py): no filterbank, results are NOT mel values
+        if (valid0) {
+            float *orow = p.out_mel + (long long)d.b * p.n_mels * (long long)p.T + d.t0;
+            for (int m = lane; m < p.n_mels; m += 32) {
+                const float2 v = tile2[4 * m];
+                orow[m * p.T] = v.x;
+                if (valid1) orow[m * p.T + 1] = v.y;
+            }
+            __syncwarp();
+        }
+#else
+        if (valid0) {
+            float *orow = p.out_mel + (long long)d.b * p.n_mels * (long long)p.T + d.t0;
             const int4 *ent4 = reinterpret_cast<const int4 *>(s_ent) + lane;
             const float4 *wbase = reinterpret_cast<const float4 *>(s_melw) + lane;
             const unsigned char *tile_bytes = region;
             int4 e = ent4[0];  // {lo, groups, woff, m}; the next round's entry is fetched while this one computes
 #pragma unroll 1
             for (int r = 0; r < p.mel_rounds; ++r) {
-                const int4 cur = e;
+                const int4 ce = e;
                 if (r + 1 < p.mel_rounds) e = ent4[(r + 1) * 32];
                 float acc0 = 0.f, acc1 = 0.f;
                 PHASE_MARK(9);  // round setup
-                mel_groups<kPair, (kWarps > 16 ? 4 : 8)>(p.round_groups[r], wbase + p.round_wbase[r],
-                                                                     tile_bytes + cur.x * (kPair ? 8 : 4), acc0, acc1);
+                mel_groups<kPair, 8>(p.round_groups[r], wbase + p.round_wbase[r], tile_bytes + ce.x * (kPair ? 8 : 4), acc0, acc1);
                 PHASE_MARK(10);  // mel FMAs
                 const float y0 = epilogue(acc0, p), y1 = epilogue(acc1, p);
                 PHASE_MARK(11);  // log epilogue
-                if (cur.w >= 0) {
-                    float *o = orow + cur.w * p.T;
+                if (ce.w >= 0) {
+                    float *o = orow + ce.w * p.T;
                     o[0] = y0;
-                    if (kPair && t.valid1) o[1] = y1;
+                    if (kPair && valid1) o[1] = y1;
                 }
                 PHASE_MARK(12);  // stores
             }
             __syncwarp();  // tile reads done before the next task's transpose overwrites the region
             PHASE_MARK(13);  // final syncwarp
         }
+#endif
     }
 #ifdef B200MEL_PHASE_TIMING
     if (p.dbg && lane == 0) {

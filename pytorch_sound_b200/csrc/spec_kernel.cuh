@@ -145,17 +145,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) spec_kernel(const KParams 
                 buf[k1 * kBufStride + lane] = a[fft32_pos(k1)];
             });
             __syncwarp();
-            static_for<0, 2>([&](auto h_) {
-                constexpr int h = decltype(h_)::value;
-                float2 tw[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) a[h * 16 + i] = buf[lane * kBufStride + h * 16 + i];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) tw[i] = s_tw[(h * 16 + i) * 32 + lane];
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (h * 16 + i > 0) a[h * 16 + i] = cmul(a[h * 16 + i], tw[i]);
-            });
+            xpose_read_twiddle<16>(a, buf, s_tw, lane);
             __syncwarp();
         }
         // prefetch this warp's next task (its task index is task + stride)
