@@ -127,7 +127,7 @@ struct b200mel_plan {
 };
 
 constexpr int kMaxSmem = 232448;
-constexpr int kDefaultWarps = 16;  // 227 KB opt-in limit per CTA on sm_100
+constexpr int kDefaultWarps = kMaxWarps;  // 227 KB opt-in limit per CTA on sm_100
 
 static void free_mel_tables(b200mel_plan *pl) {
     cudaFree(pl->d_mel_entries);
@@ -290,6 +290,7 @@ static int upload_filterbank(b200mel_plan *pl, const float *W, int n_mels, int F
     pl->mel_w_len = (int)w.size();
     return layout_smem(pl);
 }
+
 
 typedef void (*kernel_fn)(const KParams);
 // Mel kernels: {pair, split} x {magnitude, power} x {all bins, bins < 384 (pair only)}, 16 warps per CTA; the

@@ -41,7 +41,17 @@
 
 namespace b200mel {
 
-constexpr int kMaxWarps = 16;   // warps per CTA of the mel kernel (register budget 65536 / (32 * 16) = 128)
+#ifndef B200MEL_WARPS_PER_CTA
+#define B200MEL_WARPS_PER_CTA 16
+#endif
+// warps per CTA of the mel kernel: 16 -> 128 registers per thread, 20 -> 96 (register budget 65536 / (32 * warps))
+constexpr int kMaxWarps = B200MEL_WARPS_PER_CTA;
+#ifndef B200MEL_MEL_CHUNK
+#define B200MEL_MEL_CHUNK (B200MEL_WARPS_PER_CTA > 16 ? 4 : 8)
+#endif
+#ifndef B200MEL_XPOSE_BATCH
+#define B200MEL_XPOSE_BATCH (B200MEL_WARPS_PER_CTA > 16 ? 8 : 16)
+#endif
 // float2 per transposed row: 272 B = 17 x 16 B, so a lane reads ITS row with 128-bit loads (two values per LDS)
 // and the 8 lanes of a quarter warp hit 8 different 16-byte bank groups (17 l mod 8 = l); the write side stores
 // 32 consecutive float2 per row, conflict-free for any stride.
@@ -84,6 +94,9 @@ struct KParams {
     // outputs
     float *out_mel, *out_a, *out_b;
     long long *dbg;  // phase-timing accumulators (debug builds only)
+#ifdef B200MEL_X_MELLITE_LDC
+    float xw[64];    // probe: weights read from the kernel-parameter constant bank
+#endif
     float mag_eps;
     // branch-free epilogue: y = min(max(lg2(max(x, floor) + offset) * log_scale, lo), hi) * norm_scale + norm_bias
     int use_log;
@@ -102,8 +115,10 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Waits for the phase with the given parity.  The spin is bounded (seconds): a protocol bug or a lost bulk copy ends in
+// a trap, i.e. a CUDA error on the host, instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
+    uint32_t done, spins = 0;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -112,6 +127,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
+        if (!done && ++spins > (1u << 24)) __trap();
     } while (!done);
 }
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
@@ -313,6 +329,109 @@ struct Desc {
     unsigned flags;   // 1: frame t0 exists, 2: frame t0+1 exists (pair mode), 4: span leaves [0, Li) (reflect patch)
 };
 
+// Locate a task and (one elected lane) request its samples: arm the warp's mbarrier and issue ONE bulk copy of
+// the in-range part of the span, widened to 16-byte boundaries on both sides (the extra <= 3 floats per side
+// are never read as samples: interior tasks ignore them, edge tasks overwrite the halo after the copy landed).
+// Everything is computed uniformly by all lanes in straight-line code, so the scheduler can sink it into the
+// shadow of the surrounding FFT arithmetic; only the three PTX instructions at the end are predicated.
+template <bool kPair>
+__device__ __forceinline__ Desc request_task(const KParams &p, int b, int q, int lane, uint32_t stage_s, uint32_t bar) {
+    Desc d;
+    d.b = b;
+    int Li = p.L, Ti = p.T;
+    if (p.lengths) {
+        Li = min(__ldg(p.lengths + b), p.L);
+        Ti = min(frames_of(Li, p.n_fft, p.hop, p.pad), p.T);
+    }
+    d.Li = Li;
+    d.t0 = q * p.pair_frames;
+    const bool v0 = d.t0 < Ti, v1 = kPair && p.pair_frames == 2 && d.t0 + 1 < Ti;
+    const int s_first = d.t0 * p.hop - p.pad;
+    const int span = p.n_fft + (v1 ? p.hop : 0);
+    const int p_lo = max(s_first, 0), p_hi = min(s_first + span, Li);
+    const uintptr_t src = reinterpret_cast<uintptr_t>(p.wav + (long long)b * p.row_stride + p_lo);
+    const int mis = (int)(src >> 2) & 3;   // floats by which the first in-range sample misses a 16-byte boundary
+    const int off = p_lo - s_first;        // its position in the span
+    d.delta = (mis - off) & 3;             // shift that makes stage and global address 16-byte congruent
+    d.flags = (v0 ? 1u : 0u) | (v1 ? 2u : 0u) | ((s_first < 0 || s_first + span > Li) ? 4u : 0u);
+    if (v0 && lane == 0) {
+        const uint32_t bytes = (uint32_t)(((p_hi - p_lo + mis) * 4 + 15) & ~15);
+#ifndef B200MEL_X_NOFENCE  // probe: cost of the proxy fence (unsafe)
+        fence_proxy_async();
+#endif
+        mbar_arrive_expect_tx(bar, bytes);
+        tma_load_1d(stage_s + (uint32_t)((off + d.delta - mis) * 4), reinterpret_cast<const void *>(src - 4 * mis), bytes, bar);
+    }
+    return d;
+}
+
+// Reflected halo of an edge task (<= 4 of 44 tasks per 1-s clip): the out-of-range part of the span is filled
+// after the bulk copy has landed.  The reflected samples are almost always inside the staged in-range part, so
+// they are copied within shared memory; only a reflection that leaves the span falls back to global memory.
+__device__ __forceinline__ void patch_halo_smem(const KParams &p, const Desc &d, float *stage, int lane) {
+    const int s_first = d.t0 * p.hop - p.pad;
+    const int span = p.n_fft + ((d.flags & 2u) ? p.hop : 0);
+    const int p_lo = max(s_first, 0), p_hi = min(s_first + span, d.Li);
+    const float *row = p.wav + (long long)d.b * p.row_stride;
+    float *st = stage + d.delta - s_first;  // st[s] = sample at padded-coordinate position s
+    for (int s = s_first + lane; s < 0; s += 32) {
+        const int r = reflect_index(s, d.Li);
+        st[s] = (r >= p_lo && r < p_hi) ? st[r] : __ldg(row + r);
+    }
+    for (int s = d.Li + lane; s < s_first + span; s += 32) {
+        const int r = reflect_index(s, d.Li);
+        st[s] = (r >= p_lo && r < p_hi) ? st[r] : __ldg(row + r);
+    }
+    __syncwarp();
+}
+
+// Pair mode, stage -> registers with the window applied: a[j] = {x_t[32 j + lane], x_t+1[32 j + lane]} * w[32 j + lane].
+// hann_cs = (0.25 cos phi, 0.25 sin phi), phi = 2 pi lane / 1024 (only read when p.hann_full).
+__device__ __forceinline__ void load_windowed_pair(float2 *a, const float *x0, const float *s_win, float2 hann_cs,
+                                                   const KParams &p, int lane, bool valid1) {
+    // keep the generated window a per-task computation: hoisted out of the task loop it would be 32 live registers
+    // (in practice 32 local-memory reloads per task, i.e. the table loads this path exists to avoid)
+    asm volatile("" : "+f"(hann_cs.x), "+f"(hann_cs.y));
+    if (valid1 && p.hop == 256) {
+        // hop = 8 * 32: element j of frame t+1 IS element j+8 of frame t in the stage -> 40 distinct
+        // shared-memory loads per lane for the two frames instead of 64 (the kernel is LSU-bound)
+        float raw[40];
+#pragma unroll
+        for (int j = 0; j < 40; ++j) raw[j] = x0[32 * j];
+        if (p.hann_full) {
+            // Full-length periodic Hann generated in registers: 0.5 w[32 j + lane] = 0.25 - 0.25 cos(theta_j + phi),
+            // theta_j = 2 pi j / 32 (compile-time cos / sin), so no window-table loads on the common path.
+            static_for<0, 16>([&](auto j_) {
+                constexpr int j = decltype(j_)::value;
+                // t = 0.25 cos(theta_j + phi); TwConst::s32 holds -sin
+                const float t = fmaf(TwConst::s32[j], hann_cs.y, TwConst::c32[j] * hann_cs.x);
+                const float w0 = 0.25f - t, w1 = 0.25f + t;  // slots j and j + 16 (theta + pi)
+                a[j] = __fmul2_rn(make_float2(raw[j], raw[j + 8]), make_float2(w0, w0));
+                a[j + 16] = __fmul2_rn(make_float2(raw[j + 16], raw[j + 24]), make_float2(w1, w1));
+            });
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float w = s_win[32 * j + lane];
+                a[j] = __fmul2_rn(make_float2(raw[j], raw[j + 8]), make_float2(w, w));
+            }
+        }
+    } else if (valid1) {
+        const float *x1 = x0 + p.hop;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float w = s_win[32 * j + lane];
+            a[j] = __fmul2_rn(make_float2(x0[32 * j], x1[32 * j]), make_float2(w, w));  // one FMUL2
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            a[j].x = x0[32 * j] * s_win[32 * j + lane];
+            a[j].y = 0.f;
+        }
+    }
+}
+
 // kPower: 1 magnitude, 2 power.  kTop: 32-bin groups of the spectrum that are separated in pair mode — 16 = all
 // 513 bins, 12 = bins 0..383 only (plans whose filterbank ends below bin 384, e.g. fmax 8000 Hz at 22050 Hz; the
 // unused FFT outputs are dead code for the compiler).  16 warps per CTA (128 registers per thread).
@@ -351,38 +470,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
     int cb = (int)(task / p.tasks_per_clip);
     int cq = (int)(task - (long long)cb * p.tasks_per_clip);
 
-    // Locate a task and (one elected lane) request its samples: arm the warp's mbarrier and issue ONE bulk copy of
-    // the in-range part of the span, widened to 16-byte boundaries on both sides (the extra <= 3 floats per side
-    // are never read as samples: interior tasks ignore them, edge tasks overwrite the halo after the copy landed).
-    // Everything is computed uniformly by all lanes in straight-line code, so the scheduler can sink it into the
-    // shadow of the surrounding FFT arithmetic; only the three PTX instructions at the end are predicated.
-    auto request = [&](int b, int q) -> Desc {
-        Desc d;
-        d.b = b;
-        int Li = p.L, Ti = p.T;
-        if (p.lengths) {
-            Li = min(__ldg(p.lengths + b), p.L);
-            Ti = min(frames_of(Li, p.n_fft, p.hop, p.pad), p.T);
-        }
-        d.Li = Li;
-        d.t0 = q * p.pair_frames;
-        const bool v0 = d.t0 < Ti, v1 = kPair && p.pair_frames == 2 && d.t0 + 1 < Ti;
-        const int s_first = d.t0 * p.hop - p.pad;
-        const int span = p.n_fft + (v1 ? p.hop : 0);
-        const int p_lo = max(s_first, 0), p_hi = min(s_first + span, Li);
-        const uintptr_t src = reinterpret_cast<uintptr_t>(p.wav + (long long)b * p.row_stride + p_lo);
-        const int mis = (int)(src >> 2) & 3;   // floats by which the first in-range sample misses a 16-byte boundary
-        const int off = p_lo - s_first;        // its position in the span
-        d.delta = (mis - off) & 3;             // shift that makes stage and global address 16-byte congruent
-        d.flags = (v0 ? 1u : 0u) | (v1 ? 2u : 0u) | ((s_first < 0 || s_first + span > Li) ? 4u : 0u);
-        if (v0 && lane == 0) {
-            const uint32_t bytes = (uint32_t)(((p_hi - p_lo + mis) * 4 + 15) & ~15);
-            fence_proxy_async();
-            mbar_arrive_expect_tx(bar, bytes);
-            tma_load_1d(stage_s + (uint32_t)((off + d.delta - mis) * 4), reinterpret_cast<const void *>(src - 4 * mis), bytes, bar);
-        }
-        return d;
-    };
+    auto request = [&](int b, int q) -> Desc { return request_task<kPair>(p, b, q, lane, stage_s, bar); };
 
     // Prologue, ordered for programmatic dependent launch (PDL): everything that does not touch caller memory —
     // mbarrier init and the fetch of the plan-owned tables — is started BEFORE griddepcontrol.wait, i.e. it overlaps
@@ -458,25 +546,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
     }
 #endif
 
-    // Reflected halo of an edge task (<= 4 of 44 tasks per 1-s clip): the out-of-range part of the span is filled
-    // after the bulk copy has landed.  The reflected samples are almost always inside the staged in-range part, so
-    // they are copied within shared memory; only a reflection that leaves the span falls back to global memory.
-    auto patch_halo = [&](const Desc &d) {
-        const int s_first = d.t0 * p.hop - p.pad;
-        const int span = p.n_fft + ((d.flags & 2u) ? p.hop : 0);
-        const int p_lo = max(s_first, 0), p_hi = min(s_first + span, d.Li);
-        const float *row = p.wav + (long long)d.b * p.row_stride;
-        float *st = stage + d.delta - s_first;  // st[s] = sample at padded-coordinate position s
-        for (int s = s_first + lane; s < 0; s += 32) {
-            const int r = reflect_index(s, d.Li);
-            st[s] = (r >= p_lo && r < p_hi) ? st[r] : __ldg(row + r);
-        }
-        for (int s = d.Li + lane; s < s_first + span; s += 32) {
-            const int r = reflect_index(s, d.Li);
-            st[s] = (r >= p_lo && r < p_hi) ? st[r] : __ldg(row + r);
-        }
-        __syncwarp();
-    };
+    auto patch_halo = [&](const Desc &d) { patch_halo_smem(p, d, stage, lane); };
 
     for (; task < p.n_tasks; task += stride) {
         const Desc d = cur;
@@ -490,48 +560,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
         if (valid0) {
             PHASE_MARK(1);  // decode
             // -------------------------------------------------------------- stage -> registers, windowed
+#ifndef B200MEL_X_NOWAIT  // probe: how much of a task is spent waiting for its samples (wrong results)
             mbar_wait(bar, parity);
+#endif
             parity ^= 1;
             if (d.flags & 4u) patch_halo(d);
             const float *x0 = stage + d.delta + lane;
             PHASE_MARK(2);  // wait for the TMA stage
             if constexpr (kPair) {
-                if (valid1 && p.hop == 256) {
-                    // hop = 8 * 32: element j of frame t+1 IS element j+8 of frame t in the stage -> 40 distinct
-                    // shared-memory loads per lane for the two frames instead of 64 (the kernel is LSU-bound)
-                    float raw[40];
-#pragma unroll
-                    for (int j = 0; j < 40; ++j) raw[j] = x0[32 * j];
-                    if (p.hann_full) {
-                        static_for<0, 16>([&](auto j_) {
-                            constexpr int j = decltype(j_)::value;
-                            // t = 0.25 cos(theta_j + phi); TwConst::s32 holds -sin
-                            const float t = fmaf(TwConst::s32[j], hann_cs.y, TwConst::c32[j] * hann_cs.x);
-                            const float w0 = 0.25f - t, w1 = 0.25f + t;  // slots j and j + 16 (theta + pi)
-                            a[j] = __fmul2_rn(make_float2(raw[j], raw[j + 8]), make_float2(w0, w0));
-                            a[j + 16] = __fmul2_rn(make_float2(raw[j + 16], raw[j + 24]), make_float2(w1, w1));
-                        });
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float w = s_win[32 * j + lane];
-                            a[j] = __fmul2_rn(make_float2(raw[j], raw[j + 8]), make_float2(w, w));
-                        }
-                    }
-                } else if (valid1) {
-                    const float *x1 = x0 + p.hop;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float w = s_win[32 * j + lane];
-                        a[j] = __fmul2_rn(make_float2(x0[32 * j], x1[32 * j]), make_float2(w, w));  // one FMUL2
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        a[j].x = x0[32 * j] * s_win[32 * j + lane];
-                        a[j].y = 0.f;
-                    }
-                }
+                load_windowed_pair(a, x0, s_win, hann_cs, p, lane, valid1);
             } else {
                 const float2 *w2 = reinterpret_cast<const float2 *>(s_win);
 #pragma unroll
@@ -549,7 +586,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
                 buf[k1 * kBufStride + lane] = a[fft32_pos(k1)];
             });
             __syncwarp();
-            xpose_read_twiddle<16>(a, buf, s_tw, lane);
+            xpose_read_twiddle<B200MEL_XPOSE_BATCH>(a, buf, s_tw, lane);
             __syncwarp();  // transpose buffer is dead: magnitude tile and next stage may reuse it
             PHASE_MARK(5);  // transpose + twiddle
         }
@@ -558,7 +595,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
         cur.flags = 0;
         if (task + stride < p.n_tasks) cur = request(cb, cq);
 
+        int2 e_first = make_int2(0, -1);  // {lo, m} of the first mel round, fetched early so its latency hides under pass 2
         if (valid0) {
+#ifndef B200MEL_X_LATE_ENTRY
+            const int4 e0 = reinterpret_cast<const int4 *>(s_ent)[lane];
+            e_first = make_int2(e0.x, e0.w);
+#endif
             PHASE_MARK(6);  // prefetch issue
             fft32(a);  // pass 2: lane = k1, FFT over n2 -> Z[k1 + 32 k2] at a[pos(k2)]
             PHASE_MARK(7);  // pass 2
@@ -634,20 +676,56 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
             }
             __syncwarp();
         }
+#elif defined(B200MEL_X_MELLITE)  // cost stand-in for a lane = frame cooperative mel (wrong results): per warp and
+        // round ~29 conflict-free LDS.32 + 29 broadcast LDS.64 + 29 FFMA2, 5 epilogues with row-contiguous stores
+        if (valid0) {
+            float *orow = p.out_mel + (long long)d.b * p.n_mels * (long long)p.T + d.t0;
+            const float *tl = reinterpret_cast<const float *>(region) + lane;
+            const float2 *wq = reinterpret_cast<const float2 *>(s_melw);
+            float v[32];
+            float2 w[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = tl[k * 34];
+#ifdef B200MEL_X_MELLITE_LDC
+#pragma unroll
+            for (int k = 0; k < 32; ++k) w[k] = make_float2(p.xw[(warp * 2 + k) & 63], p.xw[(warp * 2 + k + 1) & 63]);
+#else
+#pragma unroll
+            for (int k = 0; k < 32; ++k) w[k] = wq[warp * 8 + k];
+#endif
+            float y[5];
+#pragma unroll
+            for (int sgm = 0; sgm < 5; ++sgm) {
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int k = sgm * 6; k < sgm * 6 + 6; ++k) acc = __ffma2_rn(make_float2(v[k], v[k]), w[k], acc);
+                y[sgm] = epilogue(acc.x + acc.y + v[31] * w[30 + (sgm & 1)].x, p);
+            }
+#pragma unroll
+            for (int sgm = 0; sgm < 5; ++sgm) {
+                const int m = warp * 5 + sgm;
+                if (lane < 2 && (lane == 0 || valid1)) orow[m * p.T + lane] = y[sgm];
+            }
+            __syncwarp();
+        }
 #else
         if (valid0) {
             float *orow = p.out_mel + (long long)d.b * p.n_mels * (long long)p.T + d.t0;
             const int4 *ent4 = reinterpret_cast<const int4 *>(s_ent) + lane;
             const float4 *wbase = reinterpret_cast<const float4 *>(s_melw) + lane;
             const unsigned char *tile_bytes = region;
+#ifdef B200MEL_X_LATE_ENTRY
             int4 e = ent4[0];  // {lo, groups, woff, m}; the next round's entry is fetched while this one computes
+#else
+            int4 e = make_int4(e_first.x, 0, 0, e_first.y);
+#endif
 #pragma unroll 1
             for (int r = 0; r < p.mel_rounds; ++r) {
                 const int4 ce = e;
                 if (r + 1 < p.mel_rounds) e = ent4[(r + 1) * 32];
                 float acc0 = 0.f, acc1 = 0.f;
                 PHASE_MARK(9);  // round setup
-                mel_groups<kPair, 8>(p.round_groups[r], wbase + p.round_wbase[r], tile_bytes + ce.x * (kPair ? 8 : 4), acc0, acc1);
+                mel_groups<kPair, B200MEL_MEL_CHUNK>(p.round_groups[r], wbase + p.round_wbase[r], tile_bytes + ce.x * (kPair ? 8 : 4), acc0, acc1);
                 PHASE_MARK(10);  // mel FMAs
                 const float y0 = epilogue(acc0, p), y1 = epilogue(acc1, p);
                 PHASE_MARK(11);  // log epilogue
