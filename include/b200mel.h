@@ -150,6 +150,23 @@ int b200mel_forward(const b200mel_plan *plan, const float *wav, int64_t B, int64
 int b200mel_forward_host(b200mel_plan *plan, const float *wav_host, int64_t B, int64_t L, int64_t row_stride,
                          const b200mel_epilogue *epi, float *out_mel_host, void *stream);
 
+/* ---- the small operators either side of the spectral path (device pointers, one launch each unless noted) ----
+ *
+ * b200mel_preemphasis  <- models/sound.py:66-81 PreEmphasis.forward: y[n] = x[n] - coef * x[n-1] with the
+ *                         reference's 1-sample reflect pad on the left (y[0] = x[0] - coef * x[1]).  Rows of L
+ *                         samples at x + r * x_row_stride -> y + r * y_row_stride; y must not alias x.
+ * b200mel_volume_norm  <- utils/calculate.py:56-63 volume_norm_log_torch: y = x / (std(x) / 10^(target_db/10)),
+ *                         std = unbiased standard deviation over all n elements (torch.std).  `scratch` is a
+ *                         device buffer of 2 doubles owned by the caller; two launches (moments, scale).
+ * b200mel_mel_to_mfcc  <- models/transforms.py:419-430 MelToMFCC.forward: out (B, n_mfcc, T) =
+ *                         dct (n_mfcc, n_mels) @ mel (B, n_mels, T); dct is a device pointer (the module's
+ *                         `dct_mat` buffer, torchaudio.functional.create_dct transposed, :427). */
+int b200mel_preemphasis(const float *x, int64_t B, int64_t L, int64_t x_row_stride, float coef, float *y,
+                        int64_t y_row_stride, void *stream);
+int b200mel_volume_norm(const float *x, int64_t n, float target_db, float *y, double *scratch, void *stream);
+int b200mel_mel_to_mfcc(const float *mel, const float *dct, int64_t B, int32_t n_mels, int32_t n_mfcc, int64_t T,
+                        float *out, void *stream);
+
 /* Number of kernel launches issued through this library since load (all plans;
  * used by bench.py's gpu_launches claim). */
 int64_t b200mel_launch_count(void);

@@ -241,6 +241,64 @@ def hifi_mel_spectrogram(wav, sampling_rate=22050, n_fft=1024, window_size=1024,
 
 # ---------------------------------------------------------------------------------------------
 # float32 "reference as it would run" (torch CPU) — also the timed CPU baseline
+
+# ---------------------------------------------------------------------------------------------
+# torchaudio-wrapping variant and the operators either side of the spectral path
+# ---------------------------------------------------------------------------------------------
+def log_mel_spectrogram_torchaudio(wav, sample_rate, mel_size, n_fft, win_length, hop_length, min_db, max_db,
+                                   mel_min=0.0, mel_max=None, log_offset=1e-6, dtype=np.float64):
+    """LogMelSpectrogramTorchAudio (models/transforms.py:369-394).  The arithmetic lives in torchaudio 0.7.0
+    (requirements.txt:3, not vendored): transforms.MelSpectrogram defaults = Spectrogram(power=2.0, centre reflect
+    pad n_fft//2, window zero-padded to n_fft) and MelScale = create_fb_matrix with the HTK scale, no area norm,
+    all_freqs = linspace(0, sample_rate // 2, n_fft // 2 + 1), f_max default float(sample_rate // 2).  Then
+    log(mel + log_offset) and an unconditional clamp to [ln 10^(min_db/10), ln 10^(max_db/10)]."""
+    spec = stft_complex(wav, n_fft, hop_length, win_length, pad=n_fft // 2, dtype=dtype)
+    power = spec.real ** 2 + spec.imag ** 2
+    f_max = float(mel_max) if mel_max is not None else float(sample_rate // 2)
+    fb = mel_filterbank(2 * (sample_rate // 2), n_fft, mel_size, mel_min, f_max, htk=True, norm=None).astype(dtype)
+    mel = np.einsum("mf,bft->bmt", fb, power)
+    return np.clip(np.log(mel + log_offset), db2log(min_db), db2log(max_db))
+
+
+def pre_emphasis(x, coef=0.97):
+    """PreEmphasis.forward (models/sound.py:66-81) on (B, L): one reflected sample on the left, then the 2-tap
+    cross-correlation with [-coef, 1]: y[n] = x[n] - coef x[n-1], y[0] = x[0] - coef x[1]."""
+    x = np.asarray(x, dtype=np.float64)
+    prev = np.concatenate([x[..., 1:2], x[..., :-1]], axis=-1)
+    return x - coef * prev
+
+
+def volume_norm_log(x, target_db=-11.5):
+    """volume_norm_log / volume_norm_log_torch (utils/calculate.py:46-63): np.std is the population std (ddof 0),
+    torch.std the unbiased one (ddof 1) — `ddof` picks which twin is restated."""
+    x = np.asarray(x, dtype=np.float64)
+    return x / (np.std(x) / 10 ** (target_db / 10))
+
+
+def volume_norm_log_torch(x, target_db=-11.5):
+    x = np.asarray(x, dtype=np.float64)
+    return x / (np.std(x, ddof=1) / 10 ** (target_db / 10))
+
+
+def create_dct(n_mfcc, n_mels, norm="ortho"):
+    """torchaudio.functional.create_dct (0.7.0), the (n_mels, n_mfcc) DCT-II matrix MelToMFCC transposes
+    (models/transforms.py:427)."""
+    n = np.arange(float(n_mels))
+    k = np.arange(float(n_mfcc))[:, None]
+    dct = np.cos(np.pi / float(n_mels) * (n + 0.5) * k)  # (n_mfcc, n_mels)
+    if norm is None:
+        dct *= 2.0
+    else:
+        dct[0] *= 1.0 / np.sqrt(2.0)
+        dct *= np.sqrt(2.0 / float(n_mels))
+    return dct.T
+
+
+def mel_to_mfcc(mel, n_mfcc, norm="ortho"):
+    """MelToMFCC.forward (models/transforms.py:428-430): dct_mat (n_mfcc, n_mels) @ mel (B, n_mels, T)."""
+    mel = np.asarray(mel, dtype=np.float64)
+    return np.einsum("cm,bmt->bct", create_dct(n_mfcc, mel.shape[1], norm).T, mel)
+
 # ---------------------------------------------------------------------------------------------
 class TorchReference:
     """The reference modules' op sequences on torch-CPU float32, with today's torch API

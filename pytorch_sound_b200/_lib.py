@@ -50,6 +50,11 @@ SYMBOLS = {
     "b200mel_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.POINTER(Epilogue),
                                        C.c_void_p, C.c_void_p]),
     "b200mel_launch_count": (C.c_int64, []),
+    "b200mel_preemphasis": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_int64,
+                                      C.c_void_p]),
+    "b200mel_volume_norm": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200mel_mel_to_mfcc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
+                                      C.c_void_p]),
 }
 
 _lib = None

@@ -25,6 +25,7 @@
 #include "fft32.cuh"
 #include "logmel_kernel.cuh"
 #include "spec_kernel.cuh"
+#include "wave_ops.cuh"
 
 namespace b200mel {
 
@@ -629,6 +630,78 @@ int b200mel_forward_host(b200mel_plan *pl, const float *wav_host, int64_t B, int
     if ((e = cudaMemcpyAsync(out_mel_host, pl->d_stage_out, out_bytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
         return cuda_fail(e, "cudaMemcpyAsync(D2H)");
     return B200MEL_OK;
+}
+
+static int grid_for(long long work_items, int block, int sms) {
+    long long g = (work_items + block - 1) / block;
+    const long long cap = (long long)sms * 8;  // a few waves of resident CTAs, grid-stride beyond that
+    if (g > cap) g = cap;
+    return (int)(g < 1 ? 1 : g);
+}
+static int current_sms(int *sms) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B200MEL_ENODEV, "no CUDA device (there is no CPU fallback)");
+    }
+    return B200MEL_OK;
+}
+
+int b200mel_preemphasis(const float *x, int64_t B, int64_t L, int64_t x_row_stride, float coef, float *y,
+                        int64_t y_row_stride, void *stream) {
+    if (B < 0 || L < 0) return fail(B200MEL_EINVAL, "preemphasis: negative shape");
+    if (B == 0 || L == 0) return B200MEL_OK;
+    if (!x || !y) return fail(B200MEL_EINVAL, "preemphasis: null pointer");
+    if (L < 2) return fail(B200MEL_EINVAL, "preemphasis: reflect padding needs L >= 2 (models/sound.py:80)");
+    if (x_row_stride < L || y_row_stride < L || L > 0x7ffffff0) return fail(B200MEL_EINVAL, "preemphasis: bad stride / length");
+    int sms = 0;
+    if (int rc = current_sms(&sms)) return rc;
+    const dim3 grid((unsigned)((L + 1023) / 1024), (unsigned)(B < 65535 ? B : 65535));
+    (void)sms;
+    preemph_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, B, (int)L, x_row_stride, y_row_stride, coef);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? B200MEL_OK : cuda_fail(e, "preemphasis launch");
+}
+
+int b200mel_volume_norm(const float *x, int64_t n, float target_db, float *y, double *scratch, void *stream) {
+    if (n < 0) return fail(B200MEL_EINVAL, "volume_norm: negative size");
+    if (n == 0) return B200MEL_OK;
+    if (!x || !y || !scratch) return fail(B200MEL_EINVAL, "volume_norm: null pointer");
+    int sms = 0;
+    if (int rc = current_sms(&sms)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * sizeof(double), st);
+    if (e != cudaSuccess) return cuda_fail(e, "volume_norm memset");
+    const int grid = grid_for(n, 256, sms);
+    moments_kernel<<<grid, 256, 0, st>>>(x, n, scratch);
+    // x / (std / 10^(dB/10)): the reference applies the 10^(dB/10) power ratio to an amplitude, kept as is
+    scale_by_std_kernel<<<grid, 256, 0, st>>>(x, y, n, scratch, powf(10.f, target_db / 10.f));
+    g_launches.fetch_add(2);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? B200MEL_OK : cuda_fail(e, "volume_norm launch");
+}
+
+int b200mel_mel_to_mfcc(const float *mel, const float *dct, int64_t B, int32_t n_mels, int32_t n_mfcc, int64_t T,
+                        float *out, void *stream) {
+    if (B < 0 || T < 0 || n_mels <= 0 || n_mfcc <= 0) return fail(B200MEL_EINVAL, "mel_to_mfcc: bad shape");
+    if (B == 0 || T == 0) return B200MEL_OK;
+    if (!mel || !dct || !out) return fail(B200MEL_EINVAL, "mel_to_mfcc: null pointer");
+    const size_t sm = (size_t)((n_mels + 3) & ~3) * n_mfcc * 4;
+    if (n_mels > 128 || sm > 48 * 1024 || T > 0x7fffffff)
+        return fail(B200MEL_EUNSUP, "mel_to_mfcc: supports n_mels <= 128 and a DCT matrix of at most 48 KB");
+    int sms = 0;
+    if (int rc = current_sms(&sms)) return rc;
+    const int grid = grid_for(B * T * ((n_mfcc + kDctRows - 1) / kDctRows), 128, sms);  // a thread = one column x 8 rows
+    if (n_mels <= 80)
+        dct_kernel<80><<<grid, 128, sm, (cudaStream_t)stream>>>(mel, dct, out, B, n_mels, n_mfcc, (int)T);
+    else
+        dct_kernel<128><<<grid, 128, sm, (cudaStream_t)stream>>>(mel, dct, out, B, n_mels, n_mfcc, (int)T);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? B200MEL_OK : cuda_fail(e, "mel_to_mfcc launch");
 }
 
 }  // extern "C"

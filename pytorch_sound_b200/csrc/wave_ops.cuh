@@ -1,0 +1,126 @@
+// wave_ops.cuh — the small operators either side of the spectral path (sm_100a):
+//   pre-emphasis        y[n] = x[n] - c x[n-1], y[0] = x[0] - c x[1]      models/sound.py:66-81 (PreEmphasis.forward)
+//   RMS volume norm     y = x / (std(x) / 10^(dB/10)), std over the tensor utils/calculate.py:56-63 (volume_norm_log_torch)
+//   mel -> MFCC         out[b, c, t] = sum_m dct[c, m] mel[b, m, t]       models/transforms.py:419-430 (MelToMFCC.forward)
+// All three are HBM-bound streaming kernels (8, 8 and 4 (M + C) / M bytes per element); grids are sized in
+// multiples of the SM count and every global access is a full 128-byte line per warp.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200mel {
+
+// One CTA row-strip per (sample block, clip): thread i of a block handles samples n, n + 256, n + 512, n + 768 of a
+// row, so every load / store instruction of a warp covers one contiguous 128-byte line whatever the row alignment
+// (22050-sample rows are only 8-byte aligned).  The left neighbour x[n-1] comes from the same or the previous line
+// (L1 hit), so DRAM sees each sample once: 4 bytes read + 4 bytes written per sample.
+__global__ void __launch_bounds__(256) preemph_kernel(const float *__restrict__ x, float *__restrict__ y, long long B,
+                                                       int L, long long xs, long long ys, float coef) {
+    const int n0 = blockIdx.x * 1024 + threadIdx.x;
+    for (long long b = blockIdx.y; b < B; b += gridDim.y) {
+        const float *xr = x + b * xs;
+        float *yr = y + b * ys;
+        float v[4], p[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + 256 * j;
+            if (n < L) {
+                v[j] = xr[n];
+                p[j] = xr[n > 0 ? n - 1 : 1];  // F.pad(input, (1, 0), 'reflect'): the sample before x[0] is x[1]
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + 256 * j;
+            if (n < L) yr[n] = fmaf(-coef, p[j], v[j]);
+        }
+    }
+}
+
+// sum and sum of squares of a contiguous array in double precision -> acc[0], acc[1] (atomics, one per block)
+__global__ void __launch_bounds__(256) moments_kernel(const float *__restrict__ x, long long n, double *acc) {
+    double s = 0.0, q = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = (double)x[i];
+        s += v;
+        q = fma(v, v, q);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    __shared__ double ss[8], sq[8];
+    if ((threadIdx.x & 31) == 0) ss[threadIdx.x >> 5] = s, sq[threadIdx.x >> 5] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) s += ss[w], q += sq[w];
+        atomicAdd(acc, s);
+        atomicAdd(acc + 1, q);
+    }
+}
+
+// y = x * gain / std, std = unbiased standard deviation from the accumulated moments (torch.std default)
+__global__ void __launch_bounds__(256) scale_by_std_kernel(const float *__restrict__ x, float *__restrict__ y, long long n,
+                                                            const double *acc, float gain) {
+    const double mean = acc[0] / (double)n;
+    const double var = (acc[1] - (double)n * mean * mean) / (double)(n > 1 ? n - 1 : 1);
+    const float k = gain / (float)sqrt(var > 0.0 ? var : 0.0);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = x[i] * k;
+}
+
+// mel (B, M, T) -> mfcc (B, C, T).  A warp owns 32 consecutive (b, t) columns (every global access a contiguous
+// 128-byte line) and kDctRows output rows: the column's M mel values are read into registers once per warp (the
+// C / kDctRows warps that share a column block re-read them from L1/L2, the mel tensor is small), and the DCT rows
+// come from shared memory (rows padded to a multiple of 4) as 128-bit warp-wide broadcasts, one LDS.128 per 4 FFMAs.
+// Splitting the rows over warps gives the grid enough warps to hide latency (C2: 22272 columns only).  Measured:
+// 25 us at C2 — bound by the broadcast loads (a broadcast LDS.128 still costs four shared-memory wavefronts), not
+// by HBM; a register-blocked 4-column variant spilled and was no faster.
+constexpr int kDctRows = 8;
+template <int kMaxM>
+__global__ void __launch_bounds__(128) dct_kernel(const float *__restrict__ mel, const float *__restrict__ dct,
+                                                   float *__restrict__ out, long long B, int M, int C, int T) {
+    extern __shared__ __align__(16) float s_dct[];  // [C][Mp], Mp = M rounded up to 4, zero padded
+    const int Mp = (M + 3) & ~3;
+    for (int i = threadIdx.x; i < C * Mp; i += blockDim.x) {
+        const int c = i / Mp, m = i - c * Mp;
+        s_dct[i] = m < M ? dct[c * M + m] : 0.f;
+    }
+    __syncthreads();
+    const long long cols = B * (long long)T;
+    const int lane = threadIdx.x & 31;
+    const int n_cg = (C + kDctRows - 1) / kDctRows;
+    const long long n_units = ((cols + 31) / 32) * n_cg;  // (column block, row group) pairs, row group fastest
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long u = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; u < n_units; u += warps) {
+        const long long blk = u / n_cg;
+        const int c0 = (int)(u - blk * n_cg) * kDctRows;
+        const long long i = blk * 32 + lane;
+        const bool ok = i < cols;
+        const long long b = ok ? i / T : 0;
+        const int t = ok ? (int)(i - b * T) : 0;
+        const float *src = mel + (b * M) * (long long)T + t;
+        float *dst = out + (b * C) * (long long)T + t;
+        float v[kMaxM];
+#pragma unroll
+        for (int m = 0; m < kMaxM; ++m) v[m] = (m < M && ok) ? src[(long long)m * T] : 0.f;
+#pragma unroll 2
+        for (int c = c0; c < min(c0 + kDctRows, C); ++c) {
+            const float4 *w4 = reinterpret_cast<const float4 *>(s_dct + c * Mp);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int g = 0; g < kMaxM / 4; ++g) {
+                if (4 * g < M) {
+                    const float4 w = w4[g];
+                    a0 = fmaf(w.x, v[4 * g], a0);
+                    a1 = fmaf(w.y, v[4 * g + 1], a1);
+                    a2 = fmaf(w.z, v[4 * g + 2], a2);
+                    a3 = fmaf(w.w, v[4 * g + 3], a3);
+                }
+            }
+            if (ok) dst[(long long)c * T] = (a0 + a1) + (a2 + a3);
+        }
+    }
+}
+
+}  // namespace b200mel

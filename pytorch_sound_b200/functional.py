@@ -63,3 +63,65 @@ def run(plan: "_lib.Plan", wav: torch.Tensor, epi: Optional["_lib.Epilogue"], wa
             C.c_void_p(stream))
     _lib.check(rc)
     return mel, out_a, out_b
+
+
+def _check_cuda_f32(x: torch.Tensor, what: str) -> None:
+    if not isinstance(x, torch.Tensor):
+        raise TypeError(f"{what} must be a torch.Tensor")
+    if not x.is_cuda:
+        raise RuntimeError(NO_CPU_MSG)
+    if x.dtype != torch.float32:
+        raise TypeError(f"{what} must be float32, got {x.dtype}")
+    if x.requires_grad and torch.is_grad_enabled():
+        raise RuntimeError("pytorch_sound_b200 is forward-only; detach() the input or run under torch.no_grad()")
+
+
+def preemphasis(x: torch.Tensor, coef: float) -> torch.Tensor:
+    """(B, L) CUDA float32 -> y[n] = x[n] - coef x[n-1] with the reference's 1-sample reflect pad (models/sound.py:66-81)."""
+    _check_cuda_f32(x, "input")
+    if x.dim() != 2:
+        raise ValueError(f"expected (B, L), got {tuple(x.shape)}")
+    if x.shape[1] > 0 and x.stride(1) != 1:
+        x = x.contiguous()
+    B, L = x.shape
+    y = torch.empty((B, L), device=x.device, dtype=torch.float32)
+    if B == 0 or L == 0:
+        return y
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().b200mel_preemphasis(x.data_ptr(), B, L, x.stride(0) if B > 1 else L, float(coef), y.data_ptr(), L,
+                                            C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    _lib.check(rc)
+    return y
+
+
+def volume_norm(x: torch.Tensor, target_db: float) -> torch.Tensor:
+    """x / (std(x) / 10^(target_db / 10)), std over the whole tensor (utils/calculate.py:56-63)."""
+    _check_cuda_f32(x, "x")
+    xc = x.contiguous()
+    y = torch.empty_like(xc)
+    if xc.numel() == 0:
+        return y
+    scratch = torch.empty(2, device=x.device, dtype=torch.float64)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().b200mel_volume_norm(xc.data_ptr(), xc.numel(), float(target_db), y.data_ptr(), scratch.data_ptr(),
+                                            C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    _lib.check(rc)
+    return y
+
+
+def mel_to_mfcc(mel: torch.Tensor, dct: torch.Tensor) -> torch.Tensor:
+    """dct (n_mfcc, n_mels) @ mel (B, n_mels, T) -> (B, n_mfcc, T) (models/transforms.py:428-430)."""
+    _check_cuda_f32(mel, "mel_spec")
+    if mel.dim() != 3 or dct.dim() != 2 or dct.shape[1] != mel.shape[1]:
+        raise ValueError(f"expected mel (B, M, T) and dct (C, M), got {tuple(mel.shape)} and {tuple(dct.shape)}")
+    mel = mel.contiguous()
+    dct = dct.to(device=mel.device, dtype=torch.float32).contiguous()
+    B, M, T = mel.shape
+    out = torch.empty((B, dct.shape[0], T), device=mel.device, dtype=torch.float32)
+    if B == 0 or T == 0:
+        return out
+    with torch.cuda.device(mel.device):
+        rc = _lib.lib().b200mel_mel_to_mfcc(mel.data_ptr(), dct.data_ptr(), B, M, dct.shape[0], T, out.data_ptr(),
+                                            C.c_void_p(torch.cuda.current_stream(mel.device).cuda_stream))
+    _lib.check(rc)
+    return out

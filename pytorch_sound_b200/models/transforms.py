@@ -7,7 +7,9 @@ pytorch_sound/models/transforms.py — computed by the fused sm_100a kernel (lib
     STFTTorchAudio.forward    transforms.py:297-303      STFTTorchAudio.forward   -> (real, imag)
     STFTTorchAudio.transform  transforms.py:305-311      STFTTorchAudio.transform -> (mag, phase)
     Audio2Mel.forward         transforms.py:351-366      Audio2Mel.forward(audio (B,1,L))
-    MelToMFCC.forward         transforms.py:428-430      MelToMFCC.forward (small DCT matmul on the result)
+    LogMelSpectrogramTorchAudio.forward transforms.py:387-394  same kernel, power / HTK / un-normalised filterbank
+    MelToMFCC.forward         transforms.py:428-430      MelToMFCC.forward (DCT kernel on the mel tensor)
+    MFCC.forward              transforms.py:451-455      LogMelSpectrogram + the DCT kernel
 
 Inputs must be CUDA float32; there is no CPU path.  The modules are forward-only (feature
 extraction); the reference's trainable / synthesis-direction classes (LearnableSTFT, PQMF,
@@ -206,10 +208,50 @@ class Audio2Mel(_PlanUser):
         return mel
 
 
+class _Buffers(nn.Module):
+    """Name-only container so state_dict keys match the torchaudio sub-modules of the reference."""
+
+
+class LogMelSpectrogramTorchAudio(_PlanUser):
+    """Drop-in for pytorch_sound.models.transforms.LogMelSpectrogramTorchAudio (transforms.py:369-394).
+
+    The reference wraps torchaudio 0.7.0 `MelSpectrogram(..., window_fn=torch.hann_window)` with its defaults:
+    POWER spectrogram (power=2), centre reflect padding, HTK mel scale, no area normalisation — different numerics
+    from LogMelSpectrogram (magnitude, Slaney) — then `log(mel + log_offset)` and an unconditional clamp.
+    Same fused kernel here with `power=2, mel_scale=HTK, mel_norm=none`.  The buffers torchaudio registers keep
+    their state_dict names (`melfunc.spectrogram.window`, `melfunc.mel_scale.fb` with torchaudio's (n_freq, n_mels)
+    layout)."""
+
+    def __init__(self, sample_rate: int, mel_size: int, n_fft: int, win_length: int,
+                 hop_length: int, min_db: float, max_db: float,
+                 mel_min: float = 0., mel_max: float = None):
+        super().__init__()
+        self.mel_size = mel_size
+        # db to log (unconditional, unlike LogMelSpectrogram: transforms.py:380-381)
+        self.min_db = float(np.log(np.power(10, min_db / 10)))
+        self.max_db = float(np.log(np.power(10, max_db / 10)))
+        f_max = float(mel_max) if mel_max is not None else float(sample_rate // 2)  # torchaudio's default
+        sr_even = 2 * (sample_rate // 2)  # torchaudio spaces the FFT bins over [0, sample_rate // 2]
+        fb = _lib.mel_filterbank(sr_even, n_fft, mel_size, mel_min, f_max, _lib.MEL_HTK, _lib.NORM_NONE)
+        self.melfunc = _Buffers()
+        self.melfunc.spectrogram = _Buffers()
+        self.melfunc.mel_scale = _Buffers()
+        self.melfunc.spectrogram.register_buffer('window', torch.from_numpy(_lib.hann_window(win_length)))
+        self.melfunc.mel_scale.register_buffer('fb', torch.from_numpy(fb.T.copy()))
+        self._plan_kwargs = dict(sample_rate=sr_even, n_fft=n_fft, win_length=win_length, hop_length=hop_length,
+                                 n_mels=mel_size, fmin=mel_min, fmax=f_max, pad_mode=_lib.PAD_CENTER,
+                                 mel_scale=_lib.MEL_HTK, mel_norm=_lib.NORM_NONE, power=2)
+
+    def forward(self, wav: torch.Tensor, log_offset: float = 1e-6) -> torch.Tensor:
+        epi = _lib.make_epilogue(_lib.LOG_LN_OFFSET, log_offset, self.min_db, self.max_db)
+        mel, _, _ = functional.run(self._plan(wav.device), wav, epi)
+        return mel
+
+
 class MelToMFCC(nn.Module):
     """pytorch_sound.models.transforms.MelToMFCC (transforms.py:419-430): ortho DCT-II of a mel spectrogram.
-    The (n_mfcc x mel_size) matmul is a tiny post-op on the kernel's output; torchaudio's
-    functional.create_dct is restated so torchaudio is not needed."""
+    One streaming kernel over the mel tensor (b200mel_mel_to_mfcc); torchaudio's functional.create_dct is
+    restated so torchaudio is not needed."""
 
     def __init__(self, n_mfcc: int, mel_size: int, norm: str = 'ortho'):
         super().__init__()
@@ -227,7 +269,7 @@ class MelToMFCC(nn.Module):
 
     def forward(self, mel_spec: torch.Tensor) -> torch.Tensor:
         assert len(mel_spec.size()) == 3
-        return torch.matmul(self.dct_mat, mel_spec)
+        return functional.mel_to_mfcc(mel_spec, self.dct_mat)
 
 
 class MFCC(nn.Module):
@@ -251,7 +293,7 @@ class MFCC(nn.Module):
         if wav.dim() == 3 and wav.shape[1] == 1:
             wav = wav[:, 0]
         mel_spectrogram = self.mel_func(wav)
-        return torch.matmul(self.dct_mat, mel_spectrogram)
+        return functional.mel_to_mfcc(mel_spectrogram, self.dct_mat)
 
 
 class SpectrogramMasker(nn.Module):

@@ -10,9 +10,18 @@ def patch() -> bool:
         return False
     from .models import transforms as t
 
-    for name in ("STFT", "LogMelSpectrogram", "STFTTorchAudio", "Audio2Mel", "MelToMFCC"):
+    for name in ("STFT", "LogMelSpectrogram", "STFTTorchAudio", "Audio2Mel", "LogMelSpectrogramTorchAudio", "MelToMFCC",
+                 "MFCC", "SpectrogramMasker"):
         setattr(ref_t, "_reference_" + name, getattr(ref_t, name, None))
         setattr(ref_t, name, getattr(t, name))
+    try:
+        import pytorch_sound.models.sound as ref_s  # type: ignore
+        from .models import sound as snd
+
+        ref_s._reference_PreEmphasis = ref_s.PreEmphasis
+        ref_s.PreEmphasis = snd.PreEmphasis
+    except Exception:
+        pass
     try:
         import pytorch_sound.interface.hifi_gan as ref_h  # type: ignore
         from .interface import hifi_gan as h

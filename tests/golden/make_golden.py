@@ -161,5 +161,55 @@ def main():
     print("wrote", path, {k: v.shape for k, v in out.items()})
 
 
+def extras():
+    """tests/golden/reference_extra.npz: the torchaudio-wrapping LogMelSpectrogramTorchAudio (run with the
+    torchaudio of this image, whose MelSpectrogram defaults equal 0.7.0's: power 2, HTK, no norm), PreEmphasis,
+    volume_norm_log(_torch) and MelToMFCC — same shims, same unmodified reference sources."""
+    import torch
+
+    sys.path.insert(0, REF)
+    from pytorch_sound.models import transforms as T
+    from pytorch_sound.models import sound as S
+    from pytorch_sound.utils import calculate
+    from pytorch_sound import settings
+
+    from oracle import mel_oracle
+
+    torch.set_num_threads(1)
+    out = {}
+    clips = mel_oracle.synth_clips(4, 6000, 22050, seed=20261017)
+    noise = np.random.default_rng(7).uniform(-1, 1, size=(3, 4099)).astype(np.float32)
+    with torch.no_grad():
+        ta = T.LogMelSpectrogramTorchAudio(settings.SAMPLE_RATE, settings.MEL_SIZE, settings.N_FFT, settings.WIN_LENGTH,
+                                           settings.HOP_LENGTH, settings.MIN_DB, settings.MAX_DB, float(settings.MEL_MIN),
+                                           float(settings.MEL_MAX))
+        ta_w = T.LogMelSpectrogramTorchAudio(22050, 64, 1024, 800, 200, -50, 30)  # win < n_fft, f_max default
+        out["buf.ta_fb"] = ta.melfunc.mel_scale.fb.numpy()
+        out["buf.ta_window"] = ta.melfunc.spectrogram.window.numpy()
+        pe = S.PreEmphasis()
+        out["buf.flipped_filter"] = pe.flipped_filter.numpy()
+        mf = T.MelToMFCC(settings.MFCC_SIZE, settings.MEL_SIZE)
+        out["buf.dct_mat"] = mf.dct_mat.numpy()
+        lm = T.LogMelSpectrogram(settings.SAMPLE_RATE, settings.MEL_SIZE, settings.N_FFT, settings.WIN_LENGTH,
+                                 settings.HOP_LENGTH, settings.MIN_DB, settings.MAX_DB, float(settings.MEL_MIN),
+                                 float(settings.MEL_MAX))
+        for name, x in (("clips", clips), ("noise", noise)):
+            xt = torch.from_numpy(x)
+            out[f"{name}.wav"] = x
+            out[f"{name}.ta_logmel"] = ta(xt).numpy()
+            out[f"{name}.ta_logmel_win800"] = ta_w(xt).numpy()
+            out[f"{name}.preemphasis"] = pe(xt.unsqueeze(1)).numpy()
+            out[f"{name}.volume_norm_torch"] = calculate.volume_norm_log_torch(xt).numpy()
+            out[f"{name}.volume_norm_np"] = calculate.volume_norm_log(x)
+            out[f"{name}.mfcc"] = mf(lm(xt)).numpy()
+    path = os.path.join(HERE, "reference_extra.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    main()
+    if "--extras-only" not in sys.argv:
+        main()
+    else:
+        install_shims()
+    extras()

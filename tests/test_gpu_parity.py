@@ -412,3 +412,96 @@ def test_stream_ordering_with_pdl(torch_cuda):
     # back-to-back extractions into the same caching-allocator blocks
     outs = [lm(base * 0.5 + 0.25) for _ in range(8)]
     assert all(torch.equal(o, ref) for o in outs)
+
+
+# ------------------------------------------------------------------ the "next" operators
+@pytest.fixture(scope="module")
+def extra():
+    import os
+
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_extra.npz"))
+
+
+@pytest.mark.parametrize("name", ["clips", "noise"])
+def test_torchaudio_variant(torch_cuda, extra, name):
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+
+    x = extra[f"{name}.wav"]
+    m = T.LogMelSpectrogramTorchAudio(22050, 80, 1024, 1024, 256, -50, 30, 0.0, 8000.0).cuda()
+    y = m(cuda(torch, x)).cpu().numpy()
+    assert y.shape == extra[f"{name}.ta_logmel"].shape
+    assert mo.parity_error(y, extra[f"{name}.ta_logmel"]) < TOL  # the reference's own output
+    assert mo.parity_error(y, mo.log_mel_spectrogram_torchaudio(x, 22050, 80, 1024, 1024, 256, -50, 30, 0.0, 8000.0)) < TOL
+    assert np.abs(m.melfunc.mel_scale.fb.cpu().numpy() - extra["buf.ta_fb"]).max() < 1e-5  # torchaudio: fp32 mel points
+    m2 = T.LogMelSpectrogramTorchAudio(22050, 64, 1024, 800, 200, -50, 30).cuda()  # win < n_fft, hop 200, f_max default
+    y2 = m2(cuda(torch, x)).cpu().numpy()
+    assert y2.shape == extra[f"{name}.ta_logmel_win800"].shape
+    assert mo.parity_error(y2, extra[f"{name}.ta_logmel_win800"]) < TOL
+    y3 = m(cuda(torch, x), log_offset=1e-3).cpu().numpy()
+    ref3 = mo.log_mel_spectrogram_torchaudio(x, 22050, 80, 1024, 1024, 256, -50, 30, 0.0, 8000.0, log_offset=1e-3)
+    assert mo.parity_error(y3, ref3) < TOL
+
+
+@pytest.mark.parametrize("name", ["clips", "noise"])
+def test_preemphasis_and_volume_norm(torch_cuda, extra, name):
+    torch = torch_cuda
+    from pytorch_sound_b200.models.sound import PreEmphasis
+    from pytorch_sound_b200.utils.calculate import volume_norm_log_torch
+
+    x = extra[f"{name}.wav"]
+    xg = cuda(torch, x)
+    y = PreEmphasis().cuda()(xg.unsqueeze(1))
+    assert y.shape == extra[f"{name}.preemphasis"].shape
+    np.testing.assert_allclose(y.cpu().numpy(), extra[f"{name}.preemphasis"], atol=2e-7)
+    np.testing.assert_allclose(y.cpu().numpy()[:, 0], mo.pre_emphasis(x), atol=2e-7)
+    v = volume_norm_log_torch(xg)
+    np.testing.assert_allclose(v.cpu().numpy(), extra[f"{name}.volume_norm_torch"], rtol=3e-6, atol=1e-7)
+    v2 = volume_norm_log_torch(xg, target_db=-20.0).cpu().numpy()
+    np.testing.assert_allclose(v2, mo.volume_norm_log_torch(x, -20.0), rtol=3e-6, atol=1e-7)
+
+
+def test_preemphasis_shapes_and_properties(torch_cuda):
+    torch = torch_cuda
+    from pytorch_sound_b200.models.sound import PreEmphasis
+
+    pe = PreEmphasis(0.9).cuda()
+    rng = np.random.default_rng(3)
+    for B, L in [(1, 2), (3, 5), (2, 4099), (5, 22050), (7, 8001)]:  # odd / unaligned rows, shortest legal clip
+        x = rng.standard_normal((B, L)).astype(np.float32)
+        y = pe(cuda(torch, x).unsqueeze(1)).cpu().numpy()[:, 0]
+        np.testing.assert_allclose(y, mo.pre_emphasis(x, 0.9), atol=5e-7)
+    # strided rows (a view into a wider buffer) and the full C2 size: linearity and a closed-form checksum
+    wide = torch.randn(256, 22050 + 37, device="cuda")
+    x = wide[:, 5:5 + 22050]
+    y = pe(x.unsqueeze(1))[:, 0]
+    ref = x - 0.9 * torch.cat([x[:, 1:2], x[:, :-1]], dim=1)
+    assert torch.equal(y, torch.addcmul(x, torch.cat([x[:, 1:2], x[:, :-1]], dim=1), torch.tensor(-0.9, device="cuda"))) or \
+        (y - ref).abs().max().item() < 1e-6
+    assert torch.equal(pe((2 * x).unsqueeze(1))[:, 0], 2 * y)  # exact homogeneity
+    with pytest.raises(ValueError):
+        pe(torch.zeros(2, 1, 1, device="cuda"))
+    with pytest.raises(ValueError):
+        pe(torch.zeros(2, 2, 100, device="cuda"))
+    with pytest.raises(AssertionError):
+        pe(torch.zeros(2, 100, device="cuda"))
+
+
+@pytest.mark.parametrize("M,C", [(80, 40), (128, 40), (40, 13), (7, 7)])
+def test_mel_to_mfcc_kernel(torch_cuda, extra, M, C):
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+
+    rng = np.random.default_rng(M)
+    mel = (rng.standard_normal((5, M, 87)) * 4 - 3).astype(np.float32)
+    m = T.MelToMFCC(C, M).cuda()
+    y = m(cuda(torch, mel)).cpu().numpy()
+    assert y.shape == (5, C, 87)
+    assert np.abs(y - mo.mel_to_mfcc(mel, C)).max() < 1e-4  # fp32 sums of M terms of size ~10
+    if (M, C) == (80, 40):
+        np.testing.assert_allclose(m.dct_mat.cpu().numpy(), extra["buf.dct_mat"], atol=1e-6)
+        x = extra["clips.wav"]
+        mf = T.MFCC(22050, 80, 1024, 1024, 40, 256, -50, 30, 0.0, 8000.0).cuda()
+        assert np.abs(mf(cuda(torch, x)).cpu().numpy() - extra["clips.mfcc"]).max() < 1e-3
+    with pytest.raises(ValueError):
+        m(torch.zeros(2, M + 1, 5, device="cuda"))

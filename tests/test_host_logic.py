@@ -110,8 +110,8 @@ def test_mel_to_mfcc_matches_torchaudio():
     m = MelToMFCC(40, 80)
     ref = torchaudio.functional.create_dct(40, 80, "ortho").transpose(0, 1)  # models/transforms.py:427-428
     np.testing.assert_allclose(m.dct_mat.numpy(), ref.numpy(), atol=1e-6)
-    x = torch.randn(2, 80, 7)
-    np.testing.assert_allclose(m(x).numpy(), torch.matmul(ref, x).numpy(), atol=1e-5)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):  # the DCT runs as a CUDA kernel only
+        m(torch.randn(2, 80, 7))
 
 
 def test_gpu_feature_loader_layout():
@@ -219,3 +219,34 @@ def test_spectrogram_masker_matches_reference_formula():
     m = torch.nn.functional.pad(torch.nn.functional.pad(holes, [0, win // 2]), [win // 2, 0], value=1.)
     with torch.no_grad():
         assert torch.equal(sm(holes), torch.ceil(conv(m.unsqueeze(1)).squeeze(1)))
+
+
+def test_new_operator_signatures_and_buffers(built_lib):
+    """LogMelSpectrogramTorchAudio / PreEmphasis mirror the reference's constructors, buffers and state_dict keys
+    (models/transforms.py:374-386, models/sound.py:66-76); CPU tensors raise instead of falling back."""
+    import inspect
+
+    from pytorch_sound_b200.models import sound as S
+    from pytorch_sound_b200.models import transforms as T
+    from pytorch_sound_b200.utils import calculate
+
+    sig = inspect.signature(T.LogMelSpectrogramTorchAudio.__init__)
+    assert list(sig.parameters)[1:] == ["sample_rate", "mel_size", "n_fft", "win_length", "hop_length", "min_db",
+                                        "max_db", "mel_min", "mel_max"]
+    assert sig.parameters["mel_min"].default == 0. and sig.parameters["mel_max"].default is None
+    m = T.LogMelSpectrogramTorchAudio(22050, 80, 1024, 1024, 256, -50, 30, 0., 8000.)
+    assert sorted(m.state_dict()) == ["melfunc.mel_scale.fb", "melfunc.spectrogram.window"]
+    assert m.melfunc.mel_scale.fb.shape == (513, 80)
+    assert m.min_db == pytest.approx(np.log(1e-5)) and m.max_db == pytest.approx(np.log(1e3))
+    pe = S.PreEmphasis()
+    assert inspect.signature(S.PreEmphasis.__init__).parameters["coef"].default == 0.97
+    assert list(pe.state_dict()) == ["flipped_filter"] and pe.flipped_filter.shape == (1, 1, 2)
+    np.testing.assert_allclose(pe.flipped_filter.numpy().ravel(), [-0.97, 1.0], rtol=1e-7)
+    with pytest.raises(AssertionError):
+        pe(torch.zeros(2, 100))  # the reference asserts a 3-D input
+    for call in (lambda: m(torch.zeros(2, 4000)), lambda: pe(torch.zeros(2, 1, 100)),
+                 lambda: calculate.volume_norm_log_torch(torch.zeros(8))):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
+    x = np.random.default_rng(0).standard_normal(1000)
+    np.testing.assert_allclose(calculate.volume_norm_log(x, -11.5), x / (np.std(x) / 10 ** (-1.15)), rtol=1e-12)
