@@ -211,7 +211,7 @@ static int upload_filterbank(b200mel_plan *pl, const float *W, int n_mels, int F
     std::stable_sort(rows.begin(), rows.end(), [&](const Row &x, const Row &y) { return need(x) > need(y); });
     const int rounds = (n_mels + 31) / 32;
     if (rounds > kMaxMelRounds) return fail(B200MEL_EUNSUP, "filterbank: more than 256 mel rows");
-    std::vector<MelEntry> ent((size_t)rounds * 32, MelEntry{0, 0, 0, -1});
+    std::vector<MelEntry> ent((size_t)rounds * 32, MelEntry{0, -1});
     std::vector<float> w;
     uint32_t rng = 12345u;
     auto rnd = [&]() { rng = rng * 1664525u + 1013904223u; return rng >> 8; };
@@ -270,7 +270,6 @@ static int upload_filterbank(b200mel_plan *pl, const float *W, int n_mels, int F
             const Row &row = rr[i];
             MelEntry &e = ent[(size_t)r * 32 + best_lane[i]];
             e.lo = best_lo[i];
-            e.groups = need(row);
             e.m = row.m;
             for (int k = 0; k < 4 * G; ++k) {
                 const int bin = e.lo + k;

@@ -64,10 +64,9 @@ constexpr int kSplitTileLen = 1032;                       // float entries (1025
 
 constexpr int kMaxMelRounds = 8;  // 32 rows per round -> up to 256 mel rows
 
-struct MelEntry {  // one filterbank row as seen by one lane in one round
+struct MelEntry {  // one filterbank row as seen by one lane in one round; 8 bytes so a warp reads its 32 entries with
+                   // one conflict-free 64-bit load (16-byte records read field by field were 4-way conflicts)
     int lo;        // first spectrum bin of the row's read window (16-byte aligned in the tile, slid for bank spread)
-    int groups;    // float4 weight groups the row itself needs (informational; the loop runs the round's count)
-    int woff;      // unused (weights are addressed [round base + group][lane])
     int m;         // mel row index, -1 = idle lane
 };
 
@@ -598,8 +597,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
         int2 e_first = make_int2(0, -1);  // {lo, m} of the first mel round, fetched early so its latency hides under pass 2
         if (valid0) {
 #ifndef B200MEL_X_LATE_ENTRY
-            const int4 e0 = reinterpret_cast<const int4 *>(s_ent)[lane];
-            e_first = make_int2(e0.x, e0.w);
+            e_first = reinterpret_cast<const int2 *>(s_ent)[lane];
 #endif
             PHASE_MARK(6);  // prefetch issue
             fft32(a);  // pass 2: lane = k1, FFT over n2 -> Z[k1 + 32 k2] at a[pos(k2)]
@@ -711,26 +709,26 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
 #else
         if (valid0) {
             float *orow = p.out_mel + (long long)d.b * p.n_mels * (long long)p.T + d.t0;
-            const int4 *ent4 = reinterpret_cast<const int4 *>(s_ent) + lane;
+            const int2 *ent2 = reinterpret_cast<const int2 *>(s_ent) + lane;
             const float4 *wbase = reinterpret_cast<const float4 *>(s_melw) + lane;
             const unsigned char *tile_bytes = region;
 #ifdef B200MEL_X_LATE_ENTRY
-            int4 e = ent4[0];  // {lo, groups, woff, m}; the next round's entry is fetched while this one computes
+            int2 e = ent2[0];  // {lo, m}; the next round's entry is fetched while this one computes
 #else
-            int4 e = make_int4(e_first.x, 0, 0, e_first.y);
+            int2 e = e_first;
 #endif
 #pragma unroll 1
             for (int r = 0; r < p.mel_rounds; ++r) {
-                const int4 ce = e;
-                if (r + 1 < p.mel_rounds) e = ent4[(r + 1) * 32];
+                const int2 ce = e;
+                if (r + 1 < p.mel_rounds) e = ent2[(r + 1) * 32];
                 float acc0 = 0.f, acc1 = 0.f;
                 PHASE_MARK(9);  // round setup
                 mel_groups<kPair, B200MEL_MEL_CHUNK>(p.round_groups[r], wbase + p.round_wbase[r], tile_bytes + ce.x * (kPair ? 8 : 4), acc0, acc1);
                 PHASE_MARK(10);  // mel FMAs
                 const float y0 = epilogue(acc0, p), y1 = epilogue(acc1, p);
                 PHASE_MARK(11);  // log epilogue
-                if (ce.w >= 0) {
-                    float *o = orow + ce.w * p.T;
+                if (ce.y >= 0) {
+                    float *o = orow + ce.y * p.T;
                     o[0] = y0;
                     if (kPair && valid1) o[1] = y1;
                 }
