@@ -130,7 +130,8 @@ int b200mel_plan_destroy(b200mel_plan *plan);
  *   wav        device pointer, float32, B rows of L valid samples, row r at wav + r*row_stride
  *   lengths    nullable device pointer int32[B]: valid samples per clip (<= L).  Reflection happens
  *              at the clip's own end and frames t >= frames(lengths[b]) are written as 0
- *              (SpeechDataLoader.pad_collate_fn semantics, data/dataset.py:196-250).
+ *              (SpeechDataLoader.pad_collate_fn semantics, data/dataset.py:196-250).  A clip with
+ *              lengths[b] <= pad cannot be reflect-padded (the reference raises): all its frames are 0.
  *   out_mel    nullable device pointer float32 (B, n_mels, T) contiguous, T from b200mel_out_frames(L)
  *   out_a/out_b nullable, (B, n_fft/2+1, T), meaning given by spec_kind
  *   stream     CUDA stream handle (cudaStream_t) or NULL

@@ -142,9 +142,11 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     return y;
 }
 
+// Frames of a clip of Li valid samples (`lengths` mode).  A clip that is too short to be reflect-padded (Li <= pad; the
+// reference's F.pad would raise) has no frames: its rows of the output are written as zeros.
 __device__ __forceinline__ int frames_of(int Li, int n_fft, int hop, int pad) {
     int span = Li + 2 * pad - n_fft;
-    return span < 0 ? 0 : span / hop + 1;
+    return (span < 0 || Li <= pad) ? 0 : span / hop + 1;
 }
 __device__ __forceinline__ int reflect_index(int i, int Li) {
     if (i < 0) i = -i;

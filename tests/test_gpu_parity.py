@@ -505,3 +505,19 @@ def test_mel_to_mfcc_kernel(torch_cuda, extra, M, C):
         assert np.abs(mf(cuda(torch, x)).cpu().numpy() - extra["clips.mfcc"]).max() < 1e-3
     with pytest.raises(ValueError):
         m(torch.zeros(2, M + 1, 5, device="cuda"))
+
+
+def test_lengths_too_short_to_reflect_give_zero_frames(torch_cuda):
+    """`lengths[b] <= pad` cannot be reflect-padded (the reference's F.pad raises for such a clip): the kernel
+    writes that clip's frames as zeros and leaves its neighbours untouched."""
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+
+    lm = T.LogMelSpectrogram(**GEO).cuda()
+    x = mo.synth_clips(3, 4000, 22050, seed=77)
+    lens = torch.tensor([4000, 512, 3000], dtype=torch.int32, device="cuda")
+    y = lm(cuda(torch, x), lengths=lens).cpu().numpy()
+    assert np.all(y[1] == 0.0)
+    assert mo.parity_error(y[0], mo.log_mel_spectrogram(x[:1], **GEO, clamp=False)[0]) < TOL
+    ref2 = mo.log_mel_spectrogram(x[2:3, :3000], **GEO, clamp=False)[0]
+    assert mo.parity_error(y[2][:, :ref2.shape[1]], ref2) < TOL and np.all(y[2][:, ref2.shape[1]:] == 0.0)
