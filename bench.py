@@ -388,7 +388,10 @@ def main():
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": ncu_traffic() if args.workload == "C2" else None, "peak_source": peak_src, "basis": "HBM-read (4*B*L bytes per launch)",
                          "read_plus_write_frac": (bytes_read + bytes_written) / (ms_per_step * 1e-3) / 1e9 / peak,
-                         "kernel": "b200mel::logmel_kernel<%s, mel, 16 warps>" % ("pair" if N_FFT == 1024 else "split"),
+                         "kernel": "b200mel::logmel_kernel<%s, power 1, %s>, 16 warps per CTA" % (
+                             "pair" if N_FFT == 1024 else "split",
+                             "bins < 384" if N_FFT == 1024 and int(module.mel_filter.ne(0).any(0).nonzero().max()) < 384
+                             else "all bins"),
                          "avg_launch_us": ms_per_step * 1e3},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_read,
                     "d2h_bytes_per_step": bytes_written, "ms_per_step": ms_e2e, "steps": e2e_steps,

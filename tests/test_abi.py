@@ -79,6 +79,29 @@ def test_error_codes_without_gpu(built_lib):
         built_lib.check(built_lib.EINVAL)
 
 
+def test_wave_operator_argument_validation_without_gpu(built_lib):
+    """Argument checks of the waveform-side entry points happen before any CUDA call."""
+    import torch
+
+    lib = built_lib.lib()
+    buf = np.zeros(64, dtype=np.float32)
+    p = buf.ctypes.data
+    assert lib.b200mel_preemphasis(None, 1, 16, 16, 0.97, p, 16, None) == built_lib.EINVAL
+    assert lib.b200mel_preemphasis(p, 1, 1, 1, 0.97, p, 1, None) == built_lib.EINVAL  # reflect pad needs L >= 2
+    assert b"L >= 2" in lib.b200mel_last_error()
+    assert lib.b200mel_preemphasis(p, 2, 16, 8, 0.97, p, 16, None) == built_lib.EINVAL  # row stride < L
+    assert lib.b200mel_preemphasis(p, 0, 16, 16, 0.97, p, 16, None) == built_lib.OK  # empty batch: nothing to do
+    assert lib.b200mel_volume_norm(p, 8, -11.5, p, None, None) == built_lib.EINVAL
+    assert lib.b200mel_volume_norm(p, 0, -11.5, p, None, None) == built_lib.OK
+    assert lib.b200mel_mel_to_mfcc(p, p, 1, 0, 4, 4, p, None) == built_lib.EINVAL
+    assert lib.b200mel_mel_to_mfcc(p, p, 1, 200, 4, 4, p, None) == built_lib.EUNSUP  # more than 128 mel rows
+    assert lib.b200mel_mel_to_mfcc(None, p, 1, 8, 4, 4, p, None) == built_lib.EINVAL
+    if not torch.cuda.is_available():  # valid arguments, no device: loud, no fallback
+        assert lib.b200mel_preemphasis(p, 1, 16, 16, 0.97, p, 16, None) == built_lib.ENODEV
+        assert b"no CPU fallback" in lib.b200mel_last_error()
+        assert lib.b200mel_mel_to_mfcc(p, p, 1, 8, 4, 2, p, None) == built_lib.ENODEV
+
+
 def test_missing_library_fails_loudly(monkeypatch, built_lib):
     monkeypatch.setattr(built_lib, "_lib", None)
     monkeypatch.setattr(built_lib, "LIB_PATH", "/nonexistent/libb200mel.so")
