@@ -81,6 +81,19 @@ def ncu_traffic():
         return None
 
 
+def kernel_name(module):
+    """Which instantiation of the fused kernel the plan picks for this workload (informational)."""
+    kind = "pair" if N_FFT == 1024 else "split"
+    bins = "all bins"
+    try:
+        top = int(module.mel_filter.detach().cpu().ne(0).any(0).nonzero().max())
+        if N_FFT == 1024 and top < 384:
+            bins = "bins < 384"
+    except Exception:
+        pass
+    return f"b200mel::logmel_kernel<{kind}, power 1, {bins}>, 16 warps per CTA"
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons through NVML while `active` is set."""
 
@@ -388,10 +401,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": ncu_traffic() if args.workload == "C2" else None, "peak_source": peak_src, "basis": "HBM-read (4*B*L bytes per launch)",
                          "read_plus_write_frac": (bytes_read + bytes_written) / (ms_per_step * 1e-3) / 1e9 / peak,
-                         "kernel": "b200mel::logmel_kernel<%s, power 1, %s>, 16 warps per CTA" % (
-                             "pair" if N_FFT == 1024 else "split",
-                             "bins < 384" if N_FFT == 1024 and int(module.mel_filter.ne(0).any(0).nonzero().max()) < 384
-                             else "all bins"),
+                         "kernel": kernel_name(module),
                          "avg_launch_us": ms_per_step * 1e3},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_read,
                     "d2h_bytes_per_step": bytes_written, "ms_per_step": ms_e2e, "steps": e2e_steps,
