@@ -250,3 +250,61 @@ def test_new_operator_signatures_and_buffers(built_lib):
             call()
     x = np.random.default_rng(0).standard_normal(1000)
     np.testing.assert_allclose(calculate.volume_norm_log(x, -11.5), x / (np.std(x) / 10 ** (-1.15)), rtol=1e-12)
+
+
+def test_stage_request_index_algebra():
+    """Model of logmel_kernel.cuh::request_task / patch_halo_smem (the bulk-copy geometry of one task): for every
+    alignment of the clip rows, every edge case of the span and per-clip lengths, the copy must be 16-byte aligned
+    on both sides, stay inside the warp's stage (layout_smem: (span + 8) floats) and inside the clip's row, put
+    sample s at stage[s - s_first + delta], and every reflected halo sample must have a defined source."""
+    def frames_of(Li, n_fft, hop, pad):
+        span = Li + 2 * pad - n_fft
+        return 0 if (span < 0 or Li <= pad) else span // hop + 1
+
+    def reflect_index(i, Li):
+        if i < 0:
+            i = -i
+        if i >= Li:
+            i = 2 * (Li - 1) - i
+        return min(max(i, 0), Li - 1)
+
+    checked = 0
+    for n_fft, hop, pad, pair in [(1024, 256, 512, True), (1024, 256, 384, True), (1024, 300, 512, True),
+                                  (1024, 1, 512, True), (1024, 1024, 512, True), (2048, 512, 1024, False),
+                                  (2048, 512, 768, False)]:
+        pair_frames = 2 if pair else 1
+        stage_floats = ((n_fft + (hop if pair_frames == 2 else 0) + 8) * 4 + 15) // 16 * 4
+        for L in (pad + 1, pad + 2, 1500 if pad < 1500 else 2500, 4097, 6000):
+            T = (L + 2 * pad - n_fft) // hop + 1
+            if T <= 0:
+                continue
+            for Li in sorted({L, max(pad + 1, L - 3), max(pad + 1, L // 2)}):
+                Ti = min(frames_of(Li, n_fft, hop, pad), T)
+                tpc = (T + pair_frames - 1) // pair_frames
+                for base_mis in range(4):          # row base address in floats modulo 4
+                    for q in sorted({0, 1, 2, tpc // 2, max(tpc - 2, 0), tpc - 1}):
+                        t0 = q * pair_frames
+                        v0, v1 = t0 < Ti, pair and pair_frames == 2 and t0 + 1 < Ti
+                        if not v0:
+                            continue
+                        s_first = t0 * hop - pad
+                        span = n_fft + (hop if v1 else 0)
+                        p_lo, p_hi = max(s_first, 0), min(s_first + span, Li)
+                        assert p_hi > p_lo
+                        src = base_mis + p_lo      # address of the first in-range sample, in floats
+                        mis, off = src & 3, p_lo - s_first
+                        delta = (mis - off) & 3
+                        nbytes = ((p_hi - p_lo + mis) * 4 + 15) & ~15
+                        dst = off + delta - mis     # stage index the copy starts at
+                        assert dst >= 0 and dst % 4 == 0 and (src - mis) % 4 == 0 and nbytes % 16 == 0 and nbytes > 0
+                        assert dst + nbytes // 4 <= stage_floats, (n_fft, hop, pad, L, Li, q, base_mis)
+                        assert (src - mis) - base_mis >= -3   # at most 3 floats before the row start (same 16-byte line)
+                        # sample p_lo lands where the consume side expects it
+                        assert dst + mis == p_lo - s_first + delta
+                        assert 0 <= delta <= 3 and span + delta <= stage_floats
+                        # halo: every out-of-range position has a reflected source inside the clip
+                        for s in list(range(s_first, 0)) + list(range(Li, s_first + span)):
+                            r = reflect_index(s, Li)
+                            assert 0 <= r < Li
+                        checked += 1
+    assert checked > 500
