@@ -183,10 +183,17 @@ static int layout_smem(b200mel_plan *pl) {
 // warp hit 8 different 16-byte bank groups (greedy placement with restarts; residual conflicts only cost
 // replays, never correctness).  Weights are stored [round group][lane] so their 128-bit loads are
 // conflict-free by construction.
-static int upload_filterbank(b200mel_plan *pl, const float *W, int n_mels, int F) {
+struct MelSchedule {  // what upload_filterbank puts on the device (pure host data, see build_mel_schedule)
+    int top_groups = 16, rounds = 0, tile_len = 0, conflict_cost = 0;
+    int round_groups[kMaxMelRounds] = {0}, round_wbase[kMaxMelRounds] = {0};
+    std::vector<MelEntry> ent;
+    std::vector<float> w;
+};
+
+static int build_mel_schedule(bool pair, const float *W, int n_mels, int F, MelSchedule *out) {
     struct Row { int m, lo, cnt; };
-    const int align = pl->pair ? 2 : 4;  // tile elements per 16 bytes (float2 pairs vs float)
-    int tile_len = pl->pair ? kPairTileLen : kSplitTileLen;
+    const int align = pair ? 2 : 4;  // tile elements per 16 bytes (float2 pairs vs float)
+    int tile_len = pair ? kPairTileLen : kSplitTileLen;
     std::vector<Row> rows(n_mels);
     int top = 0;  // one past the highest bin any row touches
     for (int m = 0; m < n_mels; ++m) {
@@ -201,18 +208,23 @@ static int upload_filterbank(b200mel_plan *pl, const float *W, int n_mels, int F
     }
     // Pair mode with a filterbank that ends below bin 384 (e.g. fmax = 8000 Hz at 22050 Hz): the kernel variant
     // that separates only the first 12 groups of 32 bins is used, and every read window is kept below bin 384.
-    pl->top_groups = 16;
-    if (pl->pair && top <= 384 && !getenv("B200MEL_NO_PRUNE")) {
+    out->top_groups = 16;
+    if (pair && top <= 384 && !getenv("B200MEL_NO_PRUNE")) {
         bool fits = true;
         for (int m = 0; m < n_mels; ++m) fits = fits && (rows[m].cnt + 8 <= 384);
-        if (fits) pl->top_groups = 12, tile_len = 384;
+        if (fits) out->top_groups = 12, tile_len = 384;
     }
+    out->tile_len = tile_len;
     auto need = [&](const Row &r) { return (r.cnt + r.lo % align + 3) / 4; };  // groups incl. alignment lead-in
     std::stable_sort(rows.begin(), rows.end(), [&](const Row &x, const Row &y) { return need(x) > need(y); });
     const int rounds = (n_mels + 31) / 32;
     if (rounds > kMaxMelRounds) return fail(B200MEL_EUNSUP, "filterbank: more than 256 mel rows");
-    std::vector<MelEntry> ent((size_t)rounds * 32, MelEntry{0, -1});
-    std::vector<float> w;
+    out->rounds = rounds;
+    out->conflict_cost = 0;
+    std::vector<MelEntry> &ent = out->ent;
+    std::vector<float> &w = out->w;
+    ent.assign((size_t)rounds * 32, MelEntry{0, -1});
+    w.clear();
     uint32_t rng = 12345u;
     auto rnd = [&]() { rng = rng * 1664525u + 1013904223u; return rng >> 8; };
     for (int r = 0; r < rounds; ++r) {
@@ -221,8 +233,8 @@ static int upload_filterbank(b200mel_plan *pl, const float *W, int n_mels, int F
         int G = 1;
         for (int i = 0; i < n; ++i) G = std::max(G, need(rr[i]));
         if (4 * G > tile_len) return fail(B200MEL_EUNSUP, "filterbank: row longer than the magnitude tile");
-        pl->round_groups[r] = G;
-        pl->round_wbase[r] = (int)(w.size() / 4);
+        out->round_groups[r] = G;
+        out->round_wbase[r] = (int)(w.size() / 4);
         // candidate window starts of every row
         std::vector<std::vector<int>> opts(n);
         for (int i = 0; i < n; ++i) {
@@ -263,6 +275,7 @@ static int upload_filterbank(b200mel_plan *pl, const float *W, int n_mels, int F
             }
             if (cost < best_cost) best_cost = cost, best_lane = lane, best_lo = lo;
         }
+        out->conflict_cost = std::max(out->conflict_cost, best_cost);
         // weights of the round: [g][lane] float4
         const size_t base = w.size();
         w.resize(base + (size_t)G * 32 * 4, 0.f);
@@ -279,18 +292,25 @@ static int upload_filterbank(b200mel_plan *pl, const float *W, int n_mels, int F
         }
     }
     if (w.empty()) w.resize(4, 0.f);
-    free_mel_tables(pl);
-    cudaError_t e;
-    if ((e = cudaMalloc(&pl->d_mel_entries, ent.size() * sizeof(MelEntry))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
-    if ((e = cudaMalloc(&pl->d_mel_w, w.size() * sizeof(float))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
-    cudaMemcpy(pl->d_mel_entries, ent.data(), ent.size() * sizeof(MelEntry), cudaMemcpyHostToDevice);
-    e = cudaMemcpy(pl->d_mel_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(filterbank)");
-    pl->mel_rounds = rounds;
-    pl->mel_w_len = (int)w.size();
-    return layout_smem(pl);
+    return B200MEL_OK;
 }
 
+static int upload_filterbank(b200mel_plan *pl, const float *W, int n_mels, int F) {
+    MelSchedule sch;
+    if (int rc = build_mel_schedule(pl->pair, W, n_mels, F, &sch)) return rc;
+    pl->top_groups = sch.top_groups;
+    for (int r = 0; r < kMaxMelRounds; ++r) pl->round_groups[r] = sch.round_groups[r], pl->round_wbase[r] = sch.round_wbase[r];
+    free_mel_tables(pl);
+    cudaError_t e;
+    if ((e = cudaMalloc(&pl->d_mel_entries, sch.ent.size() * sizeof(MelEntry))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&pl->d_mel_w, sch.w.size() * sizeof(float))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    cudaMemcpy(pl->d_mel_entries, sch.ent.data(), sch.ent.size() * sizeof(MelEntry), cudaMemcpyHostToDevice);
+    e = cudaMemcpy(pl->d_mel_w, sch.w.data(), sch.w.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(filterbank)");
+    pl->mel_rounds = sch.rounds;
+    pl->mel_w_len = (int)sch.w.size();
+    return layout_smem(pl);
+}
 
 typedef void (*kernel_fn)(const KParams);
 // Mel kernels: {pair, split} x {magnitude, power} x {all bins, bins < 384 (pair only)}, 16 warps per CTA; the
@@ -316,6 +336,37 @@ const char *b200mel_last_error(void) { return g_err.c_str(); }
 int64_t b200mel_launch_count(void) { return g_launches.load(); }
 // debug hook, not part of include/b200mel.h: device pointer to >= 16 int64 accumulators (phase-timing builds)
 void b200mel_debug_set_buffer(long long *dev_ptr) { g_dbg = dev_ptr; }
+// debug hook, not part of include/b200mel.h (host only, no GPU): builds the banded mel schedule for a dense filterbank
+// and REPLAYS it the way the kernel's mel loop walks it — round by round, lane by lane, weight group by weight group —
+// into dense_out[n_mels][n_freq].  info[0] = bin groups the kernel separates (12 / 16), [1] = rounds, [2] = tile
+// length the read windows stay below, [3] = worst quarter-warp bank-conflict cost (4 = conflict-free),
+// [4] = 1 if any read window is misaligned or leaves the tile, [5 + r] = weight groups of round r.
+int b200mel_debug_mel_schedule(const float *W, int32_t n_mels, int32_t n_freq, int32_t pair, float *dense_out, int32_t *info) {
+    if (!W || !dense_out || !info || n_mels <= 0 || n_freq <= 0) return fail(B200MEL_EINVAL, "debug_mel_schedule: bad argument");
+    MelSchedule sch;
+    if (int rc = build_mel_schedule(pair != 0, W, n_mels, n_freq, &sch)) return rc;
+    const int align = pair ? 2 : 4;
+    info[0] = sch.top_groups, info[1] = sch.rounds, info[2] = sch.tile_len, info[3] = sch.conflict_cost, info[4] = 0;
+    for (size_t i = 0; i < (size_t)n_mels * n_freq; ++i) dense_out[i] = 0.f;
+    for (int r = 0; r < sch.rounds; ++r) {
+        info[5 + r] = sch.round_groups[r];
+        for (int lane = 0; lane < 32; ++lane) {
+            const MelEntry &e = sch.ent[(size_t)r * 32 + lane];
+            if (e.m < 0) continue;
+            if (e.lo % align || e.lo < 0 || e.lo + 4 * sch.round_groups[r] > sch.tile_len) info[4] = 1;
+            for (int g = 0; g < sch.round_groups[r]; ++g)
+                for (int k = 0; k < 4; ++k) {
+                    const float w = sch.w[((size_t)sch.round_wbase[r] + (size_t)g * 32 + lane) * 4 + k];  // kernel: wbase + round_wbase + g * 32 (float4 units)
+                    const int bin = e.lo + 4 * g + k;
+                    if (w != 0.f) {
+                        if (bin >= n_freq) info[4] = 1;
+                        else dense_out[(size_t)e.m * n_freq + bin] += w;
+                    }
+                }
+        }
+    }
+    return B200MEL_OK;
+}
 
 int b200mel_mel_filterbank(int32_t sr, int32_t n_fft, int32_t n_mels, double fmin, double fmax, int32_t mel_scale,
                            int32_t mel_norm, float *out) {
