@@ -202,6 +202,20 @@ def extras():
             out[f"{name}.volume_norm_torch"] = calculate.volume_norm_log_torch(xt).numpy()
             out[f"{name}.volume_norm_np"] = calculate.volume_norm_log(x)
             out[f"{name}.mfcc"] = mf(lm(xt)).numpy()
+        # other geometries of BASELINE.json, run by the reference itself: C5 (16 kHz, fmax = Nyquist) through
+        # LogMelSpectrogram / Audio2Mel / hifi MelSpectrogram, and a hop that is not a divisor of n_fft
+        from pytorch_sound.interface.hifi_gan import MelSpectrogram
+        x5 = mel_oracle.synth_clips(3, 8000, 16000, seed=20261017 + 5000)
+        out["c5.wav"] = x5
+        x5t = torch.from_numpy(x5)
+        out["c5.logmel_clamped"] = T.LogMelSpectrogram(16000, 80, 1024, 1024, 256, -50, 30, 0.0, 8000.0)(x5t).numpy()
+        out["c5.audio2mel"] = T.Audio2Mel(sampling_rate=16000)(x5t.unsqueeze(1)).numpy()
+        out["c5.hifi"] = MelSpectrogram(sampling_rate=16000, fmax=7600.)(x5t).numpy()
+        out["clips.logmel_hop300"] = T.LogMelSpectrogram(22050, 80, 1024, 1024, 300, None, None, 0.0, 8000.0)(
+            torch.from_numpy(clips)).numpy()
+        st = T.STFTTorchAudio(filter_length=1024, hop_length=200, win_length=800, n_fft=1024)
+        re, im = st(torch.from_numpy(clips))
+        out["clips.stfta_win800_re"], out["clips.stfta_win800_im"] = re.numpy(), im.numpy()
     path = os.path.join(HERE, "reference_extra.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in out.items()})

@@ -521,3 +521,26 @@ def test_lengths_too_short_to_reflect_give_zero_frames(torch_cuda):
     assert mo.parity_error(y[0], mo.log_mel_spectrogram(x[:1], **GEO, clamp=False)[0]) < TOL
     ref2 = mo.log_mel_spectrogram(x[2:3, :3000], **GEO, clamp=False)[0]
     assert mo.parity_error(y[2][:, :ref2.shape[1]], ref2) < TOL and np.all(y[2][:, ref2.shape[1]:] == 0.0)
+
+
+def test_other_geometries_against_reference_outputs(torch_cuda, extra):
+    """The reference's own outputs at the C5 geometry (16 kHz, fmax = Nyquist: full-spectrum kernel) through three
+    front-ends, at a hop that does not divide n_fft, and with a window shorter than n_fft."""
+    torch = torch_cuda
+    from pytorch_sound_b200.interface.hifi_gan import MelSpectrogram
+    from pytorch_sound_b200.models import transforms as T
+
+    x5 = cuda(torch, extra["c5.wav"])
+    y = T.LogMelSpectrogram(16000, 80, 1024, 1024, 256, -50, 30, 0.0, 8000.0).cuda()(x5)
+    assert mo.parity_error(y.cpu().numpy(), extra["c5.logmel_clamped"]) < TOL
+    a = T.Audio2Mel(sampling_rate=16000).cuda()(x5.unsqueeze(1))
+    assert mo.parity_error(a.cpu().numpy(), extra["c5.audio2mel"]) < TOL
+    h = MelSpectrogram(sampling_rate=16000, fmax=7600.).cuda()(x5)
+    assert mo.parity_error(h.cpu().numpy(), extra["c5.hifi"]) < TOL
+    x = cuda(torch, extra["clips.wav"])
+    y3 = T.LogMelSpectrogram(22050, 80, 1024, 1024, 300, None, None, 0.0, 8000.0).cuda()(x)
+    assert mo.parity_error(y3.cpu().numpy(), extra["clips.logmel_hop300"]) < TOL
+    re, im = T.STFTTorchAudio(filter_length=1024, hop_length=200, win_length=800, n_fft=1024).cuda()(x)
+    scale = float(np.abs(extra["clips.stfta_win800_re"]).max())
+    assert np.abs(re.cpu().numpy() - extra["clips.stfta_win800_re"]).max() < 3e-6 * scale
+    assert np.abs(im.cpu().numpy() - extra["clips.stfta_win800_im"]).max() < 3e-6 * scale
