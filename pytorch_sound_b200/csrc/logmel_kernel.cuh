@@ -1,7 +1,8 @@
-// logmel_kernel.cuh — the fused STFT -> |.| -> mel -> log kernel (sm_100a), v2.
+// logmel_kernel.cuh — the fused STFT -> |.| -> mel -> log kernel (sm_100a).
 //
-// Persistent grid: one CTA per SM, up to 16 warps per CTA, every warp an independent pipeline that
-// walks the task list with stride (#warps in the grid).  A task is one 1024-point complex FFT held in
+// Persistent grid: one CTA per SM, 16 warps per CTA, every warp an independent pipeline that walks the
+// task list with stride (#warps in the grid; the warps of a CTA take tasks gridDim apart so a partial
+// last round spreads over all SMs).  A task is one 1024-point complex FFT held in
 // registers (32 complex values per lane, two radix-32 passes, one shared-memory transpose):
 //   kPair  (n_fft = 1024): frames (2q, 2q+1) of a clip packed as re/im, separated by conjugate symmetry;
 //   !kPair (n_fft = 2048): frame q packed even/odd, finished by the real-input split pass.
@@ -9,13 +10,15 @@
 // Per-warp shared-memory region (bytes):
 //   [0, 4160)              magnitude tile   (pair: float2[520] = {|X_t[k]|, |X_t+1[k]|}; split: float[1032])
 //   [4224, 4224 + stage)   sample stage     (filled by ONE cp.async.bulk = TMA 1-D copy per task, mbarrier-signalled)
-//   [0, 8448)              transpose buffer (float2[32][33]) — overlaps both, live only between the two
+//   [0, 8704)              transpose buffer (float2[32][34]) — overlaps both, live only between the two
 //                          radix-32 passes, i.e. after the stage was consumed and before the next TMA is issued.
 // The TMA for task i+1 is issued right after the transpose of task i, so the copy lands while the warp
 // does its second FFT pass, the separation, the mel contraction and the epilogue of task i.
 //
-// CTA-shared tables (loaded once per CTA): inter-pass twiddles, window, banded mel filterbank in a
-// lane-balanced schedule (rows sorted by length, 32 rows per round, weights padded to float4 groups).
+// CTA-shared tables (fetched once per CTA by four bulk copies on one mbarrier): inter-pass twiddles, window,
+// banded mel filterbank in a lane-balanced schedule (rows sorted by length, 32 rows per round, weights padded
+// to float4 groups).  Compile-time probes (-DB200MEL_X_*) produce deliberately wrong results and exist only
+// for tools/variant_bench.py (upper bounds on what a phase can cost).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -718,6 +721,45 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
             int2 e = ent2[0];  // {lo, m}; the next round's entry is fetched while this one computes
 #else
             int2 e = e_first;
+#endif
+#ifdef B200MEL_MEL_FIXED
+            // Experiment for the next round (tools/variant_bench.py "-DB200MEL_MEL_FIXED=0x731": one hex digit per
+            // round = its weight groups, here 7, 3, 1 — nvcc splits -D values at commas): when the plan's
+            // rounds match a compile-time signature, all rounds run as ONE straight-line block — every entry and every
+            // 128-bit load is visible to the scheduler at once, so the loads of the later rounds can be issued under
+            // the arithmetic of the first (fewer serial load->use points).  Other plans take
+            // the generic loop below.  Summation order inside a round differs from the chunked generic path.
+            constexpr unsigned kSig = B200MEL_MEL_FIXED;
+            constexpr int kFixRounds = kSig > 0xfffu ? 4 : kSig > 0xffu ? 3 : kSig > 0xfu ? 2 : 1;
+            constexpr int kFix[4] = {(int)((kSig >> (4 * (kFixRounds - 1))) & 15u), kFixRounds > 1 ? (int)((kSig >> (4 * (kFixRounds - 2))) & 15u) : 0,
+                                     kFixRounds > 2 ? (int)((kSig >> (4 * (kFixRounds - 3))) & 15u) : 0, kFixRounds > 3 ? (int)(kSig & 15u) : 0};
+            bool fixed_ok = p.mel_rounds == kFixRounds;
+#pragma unroll
+            for (int r = 0; r < kFixRounds; ++r) fixed_ok = fixed_ok && p.round_groups[r] == kFix[r];
+            if (fixed_ok) {
+                int2 ents[kFixRounds];
+                float acc[kFixRounds][2];
+                ents[0] = e;
+#pragma unroll
+                for (int r = 1; r < kFixRounds; ++r) ents[r] = ent2[r * 32];
+                static_for<0, kFixRounds>([&](auto r_) {
+                    constexpr int r = decltype(r_)::value;
+                    int wb = 0;  // float4 index of the round's weights: sum of the earlier rounds' groups x 32 lanes
+#pragma unroll
+                    for (int i = 0; i < r; ++i) wb += kFix[i] * 32;
+                    acc[r][0] = acc[r][1] = 0.f;
+                    mel_round<kPair, kFix[r]>(wbase + wb, tile_bytes + ents[r].x * (kPair ? 8 : 4), acc[r][0], acc[r][1]);
+                });
+#pragma unroll
+                for (int r = 0; r < kFixRounds; ++r) {
+                    const float y0 = epilogue(acc[r][0], p), y1 = epilogue(acc[r][1], p);
+                    if (ents[r].y >= 0) {
+                        float *o = orow + ents[r].y * p.T;
+                        o[0] = y0;
+                        if (kPair && valid1) o[1] = y1;
+                    }
+                }
+            } else
 #endif
 #pragma unroll 1
             for (int r = 0; r < p.mel_rounds; ++r) {
