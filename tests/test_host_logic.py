@@ -348,3 +348,48 @@ def test_banded_mel_schedule_reproduces_the_filterbank(built_lib, cfg):
     assert fn(Wd.ctypes.data, 9, Wd.shape[1], int(pair), dense.ctypes.data, info.ctypes.data) == 0
     np.testing.assert_array_equal(dense, Wd)
     assert info[4] == 0
+
+
+def test_patch_swaps_operators_into_an_importable_pytorch_sound(monkeypatch):
+    """patch_pytorch_sound() against a stand-in `pytorch_sound` package (the real one cannot be imported on this
+    image): every operator of the path is swapped, the originals stay reachable as _reference_<Name>,
+    and a missing package means False, not an exception."""
+    import sys
+    import types
+
+    import pytorch_sound_b200
+    from pytorch_sound_b200.interface import hifi_gan as H
+    from pytorch_sound_b200.models import sound as S
+    from pytorch_sound_b200.models import transforms as T
+
+    for name in [m for m in sys.modules if m == "pytorch_sound" or m.startswith("pytorch_sound.")]:
+        monkeypatch.delitem(sys.modules, name)
+    monkeypatch.setitem(sys.modules, "pytorch_sound", None)  # import raises -> patch reports False
+    assert pytorch_sound_b200.patch_pytorch_sound() is False
+
+    names_t = ["STFT", "LogMelSpectrogram", "STFTTorchAudio", "Audio2Mel", "LogMelSpectrogramTorchAudio", "MelToMFCC",
+               "MFCC", "SpectrogramMasker"]
+    pkg = types.ModuleType("pytorch_sound")
+    models = types.ModuleType("pytorch_sound.models")
+    tr = types.ModuleType("pytorch_sound.models.transforms")
+    snd = types.ModuleType("pytorch_sound.models.sound")
+    iface = types.ModuleType("pytorch_sound.interface")
+    hg = types.ModuleType("pytorch_sound.interface.hifi_gan")
+    originals = {}
+    for n in names_t:
+        originals[n] = type(n, (), {})
+        setattr(tr, n, originals[n])
+    originals["PreEmphasis"] = type("PreEmphasis", (), {})
+    snd.PreEmphasis = originals["PreEmphasis"]
+    originals["MelSpectrogram"] = type("MelSpectrogram", (), {})
+    hg.MelSpectrogram = originals["MelSpectrogram"]
+    pkg.models, pkg.interface, models.transforms, models.sound, iface.hifi_gan = models, iface, tr, snd, hg
+    for m in (pkg, models, tr, snd, iface, hg):
+        monkeypatch.setitem(sys.modules, m.__name__, m)
+
+    assert pytorch_sound_b200.patch_pytorch_sound() is True
+    for n in names_t:
+        assert getattr(tr, n) is getattr(T, n), n
+        assert getattr(tr, "_reference_" + n) is originals[n]
+    assert snd.PreEmphasis is S.PreEmphasis and snd._reference_PreEmphasis is originals["PreEmphasis"]
+    assert hg.MelSpectrogram is H.MelSpectrogram and hg._reference_MelSpectrogram is originals["MelSpectrogram"]
