@@ -9,4 +9,6 @@ python tools/variant_bench.py "" \
     "-DB200MEL_WARPS_PER_CTA=12 -DB200MEL_MEL_FIXED=0x731" \
     "-DB200MEL_X_NOMEL"
 VB_CLIPS=2048 python tools/variant_bench.py "" "-DB200MEL_MEL_FIXED=0x731" "-DB200MEL_WARPS_PER_CTA=12 -DB200MEL_MEL_FIXED=0x731"
+VB_WORKLOAD=C4 python tools/variant_bench.py "" "-DB200MEL_SPLIT_LDS64"
+VB_WORKLOAD=C5 python tools/variant_bench.py "" "-DB200MEL_MEL_FIXED=0xa32"
 rm -f gpurun_out/*.so gpurun_out/*.pt

@@ -21,7 +21,7 @@ from pytorch_sound_b200 import _lib
 _lib.LIB_PATH = %(lib)r
 from pytorch_sound_b200.models.transforms import LogMelSpectrogram
 B, L = %(B)d, %(L)d
-m = LogMelSpectrogram(22050, 80, 1024, 1024, 256, -50, 30, 0., 8000.).cuda()
+m = LogMelSpectrogram(*%(geo)r).cuda()
 g0 = torch.Generator(device="cuda").manual_seed(1)
 xs = [torch.randn(B, L, device="cuda", generator=g0) * 0.1 for _ in range(8)]
 for x in xs: m(x)
@@ -46,8 +46,13 @@ print("%%.2f" %% best)
 
 def main():
     from pytorch_sound_b200 import build
-    B = int(os.environ.get("VB_CLIPS", "256"))
-    L = int(os.environ.get("VB_L", "22050"))
+    # VB_WORKLOAD=C2 (default) | C4 (n_fft 2048 split-mode kernel) | C5 (16 kHz, full-spectrum pair kernel)
+    wl = os.environ.get("VB_WORKLOAD", "C2")
+    geo, B0, L0 = {"C2": ((22050, 80, 1024, 1024, 256, -50, 30, 0., 8000.), 256, 22050),
+                   "C4": ((44100, 128, 2048, 2048, 512, -50, 30, 0., None), 16, 441000),
+                   "C5": ((16000, 80, 1024, 1024, 256, -50, 30, 0., 8000.), 8192, 8000)}[wl]
+    B = int(os.environ.get("VB_CLIPS", str(B0)))
+    L = int(os.environ.get("VB_L", str(L0)))
     ref = None
     for i, flags in enumerate(sys.argv[1:] or [""]):
         lib = os.path.join(ROOT, "gpurun_out", f"libb200mel_var{i}.so")
@@ -58,7 +63,7 @@ def main():
             print(f"[{flags}] BUILD FAILED\n{r.stderr[-2000:]}")
             continue
         out = os.path.join(ROOT, "gpurun_out", f"var{i}.pt")
-        r = subprocess.run([sys.executable, "-c", CHILD % dict(root=ROOT, lib=lib, out=out, B=B, L=L)],
+        r = subprocess.run([sys.executable, "-c", CHILD % dict(root=ROOT, lib=lib, out=out, B=B, L=L, geo=geo)],
                            capture_output=True, text=True)
         if r.returncode:
             print(f"[{flags}] RUN FAILED\n{r.stderr[-2000:]}")
