@@ -164,6 +164,24 @@ def synth(rank, n_batches):
     return out
 
 
+def nbuf():
+    """Distinct input/output buffer pairs the steps rotate over: enough to exceed the 126 MB L2
+    (C2: 8 x (22.6 MB in + 7.1 MB out) = 238 MB)."""
+    pair_bytes = 4 * B_PER_GPU * (L + N_MELS * T)
+    return max(2, min(8, -(-200_000_000 // pair_bytes)))
+
+
+def config_dict(world):
+    """`config` of the JSON line — the SAME dict in both arms (the driver compares them): what one step processes."""
+    n = nbuf()
+    pair_bytes = 4 * B_PER_GPU * (L + N_MELS * T)
+    return {"workload": WORKLOAD_NAME + ", LogMelSpectrogram (centre pad, ln(mel+1e-6), clamp -50/30 dB)",
+            "clips_per_gpu": B_PER_GPU, "samples_per_clip": L, "frames_per_clip": T,
+            "l2_policy": f"steps rotate over {n} distinct input/output buffer pairs "
+                         f"({n * pair_bytes / 1e6:.0f} MB > 126 MB L2)",
+            "parallelism": f"clips sharded over {world} GPU(s), no data-path collective"}
+
+
 def cpu_reference_run(steps, warmup, budget_s=100.0, full=True):
     """Time the reference's op sequence (oracle port, torch CPU fp32, all host threads).
 
@@ -178,7 +196,8 @@ def cpu_reference_run(steps, warmup, budget_s=100.0, full=True):
     torch.set_num_threads(cores)
     ref = mo.TorchReference(sample_rate=SR, mel_size=N_MELS, n_fft=N_FFT, win_length=N_FFT, hop_length=HOP,
                             min_db=-50, max_db=30, mel_min=0.0, mel_max=FMAX)
-    x = torch.from_numpy(mo.synth_clips(min(B_PER_GPU, 256), L, SR, seed=SEED))
+    xs = torch.from_numpy(synth(0, min(nbuf(), 4)))  # the same seeded batches the GPU arm rotates over
+    x = xs[0]
     with torch.no_grad():
         probe = min(16, x.shape[0])
         ref.logmel_conv(x[:probe])
@@ -186,11 +205,11 @@ def cpu_reference_run(steps, warmup, budget_s=100.0, full=True):
         ref.logmel_conv(x[:probe])
         per_clip = (time.perf_counter() - t0) / probe
         clips = int(max(1, min(x.shape[0], budget_s / max(1, steps + warmup) / per_clip)))
-        for _ in range(warmup):
-            ref.logmel_conv(x[:clips])
+        for i in range(warmup):
+            ref.logmel_conv(xs[i % len(xs)][:clips])
         t0 = time.perf_counter()
-        for _ in range(steps):
-            ref.logmel_conv(x[:clips])
+        for i in range(steps):
+            ref.logmel_conv(xs[i % len(xs)][:clips])
         dt = time.perf_counter() - t0
         value = steps * clips * L / SR / 3600.0 / dt
         alt = None
@@ -202,9 +221,9 @@ def cpu_reference_run(steps, warmup, budget_s=100.0, full=True):
                 ref.logmel_stft(x[:clips])
             alt = n_alt * clips * L / SR / 3600.0 / (time.perf_counter() - t1)
     return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{clips} of the {B_PER_GPU} clips of the workload per step x {steps} steps, conv-DFT LogMelSpectrogram "
-                      f"op sequence (oracle.TorchReference.logmel_conv), torch {torch.__version__} CPU fp32, "
-                      f"{cores} threads",
+            "sample": f"{clips} of the {B_PER_GPU} clips of the workload per step x {steps} steps, the stock op sequence of "
+                      f"LogMelSpectrogram.forward (reflect pad, conv-DFT, sqrt, atan2, mel matmul, log, clamp: "
+                      f"oracle.TorchReference.logmel_conv), torch {torch.__version__} CPU fp32, {cores} threads",
             "torch_stft_variant_value": alt, "ms_per_step": dt / steps * 1e3, "clips_per_step": clips}
 
 
@@ -218,8 +237,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAME + " (bounded sample per step)",
-                   "clips_per_step": r["clips_per_step"]},
+        "config": config_dict(max(1, args.gpus)),
+        "clips_per_step": r["clips_per_step"],
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -269,8 +288,7 @@ def main():
 
     # ---- inputs: NBUF distinct batches, > L2 in aggregate --------------------------------------------
     # enough distinct buffer pairs to exceed the 126 MB L2 (C2: 8 x (22.6 MB in + 7.1 MB out) = 238 MB)
-    pair_bytes = 4 * B_PER_GPU * (L + N_MELS * T)
-    NBUF = max(2, min(8, -(-200_000_000 // pair_bytes)))
+    NBUF = nbuf()
     host = torch.from_numpy(synth(rank, NBUF)).pin_memory()
     d_in = host.to(dev)
     outs = [None] * NBUF
@@ -393,11 +411,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME + ", LogMelSpectrogram (centre pad, ln(mel+1e-6), clamp -50/30 dB)",
-                       "clips_per_gpu": B_PER_GPU, "samples_per_clip": L, "frames_per_clip": T,
-                       "l2_policy": f"rotating over {NBUF} distinct input/output buffer pairs "
-                                    f"({NBUF * (bytes_read + bytes_written) / 1e6:.0f} MB > 126 MB L2)",
-                       "parallelism": f"clips sharded over {world} GPU(s), no data-path collective"},
+            "config": config_dict(world),
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": ncu_traffic() if args.workload == "C2" else None, "peak_source": peak_src, "basis": "HBM-read (4*B*L bytes per launch)",
                          "read_plus_write_frac": (bytes_read + bytes_written) / (ms_per_step * 1e-3) / 1e9 / peak,

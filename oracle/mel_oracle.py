@@ -322,6 +322,13 @@ class TorchReference:
         basis = np.vstack([np.real(basis[:cut]), np.imag(basis[:cut])])
         self.forward_basis = torch.FloatTensor(basis[:, None, :]) * self.window
 
+    def to(self, device):
+        """Move the registered buffers (the reference modules are plain nn.Modules and run on either device)."""
+        self.mel_filter = self.mel_filter.to(device)
+        self.window = self.window.to(device)
+        self.forward_basis = self.forward_basis.to(device)
+        return self
+
     def logmel_conv(self, wav, log_offset=1e-6):
         """STFT.transform + LogMelSpectrogram.forward (models/transforms.py:53-69,231-244)."""
         torch, F = self.torch, self.torch.nn.functional
@@ -330,6 +337,9 @@ class TorchReference:
         ft = F.conv1d(x, self.forward_basis, stride=self.hop, padding=0)
         re, im = ft.chunk(2, 1)
         mag = torch.sqrt(re ** 2 + im ** 2)
+        # STFT.transform also computes the phase (models/transforms.py:69) although LogMelSpectrogram discards
+        # it (:232): part of the stock op sequence, so it is part of what gets timed
+        self.last_phase = torch.atan2(im.data, re.data)
         mel = torch.matmul(self.mel_filter, mag)
         mel = torch.log(mel + log_offset)
         if self.min_db:

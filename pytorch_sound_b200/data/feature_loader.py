@@ -8,9 +8,20 @@ SpeechDataLoader-like iterable in the MAIN process: every batch (a list of tenso
 (utils/tensor.py:6-15) and the requested feature tensors are appended where `extra_features`
 columns would sit — after the data columns and before the trailing mask (data/dataset.py:85-93).
 """
+import inspect
 from typing import Callable, Iterable, List, Optional, Sequence, Tuple
 
 import torch
+
+
+def _accepts_lengths(mod: Callable) -> bool:
+    """Decided once from the callable's signature (nn.Module: its forward): does it take `lengths=`?"""
+    fn = mod.forward if isinstance(mod, torch.nn.Module) else mod
+    try:
+        params = inspect.signature(fn).parameters
+    except (TypeError, ValueError):
+        return False
+    return 'lengths' in params or any(p.kind is inspect.Parameter.VAR_KEYWORD for p in params.values())
 
 
 class GpuFeatureLoader:
@@ -27,9 +38,11 @@ class GpuFeatureLoader:
         self.features = list(features)
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         self.mask_index = mask_index
+        self._takes_lengths = []
         for _, mod in self.features:
             if isinstance(mod, torch.nn.Module):
                 mod.to(self.device)
+            self._takes_lengths.append(_accepts_lengths(mod))
 
     def __len__(self):
         return len(self.loader)
@@ -43,15 +56,9 @@ class GpuFeatureLoader:
         if self.mask_index is not None:
             lengths = batch[self.mask_index].to(torch.float32).sum(dim=-1).to(torch.int32)
         feats = []
-        for idx, mod in self.features:
+        for (idx, mod), takes_lengths in zip(self.features, self._takes_lengths):
             wav = batch[idx]
-            if lengths is not None:
-                try:
-                    feats.append(mod(wav, lengths=lengths))
-                    continue
-                except TypeError:
-                    pass
-            feats.append(mod(wav))
+            feats.append(mod(wav, lengths=lengths) if (lengths is not None and takes_lengths) else mod(wav))
         if self.mask_index is not None:
             m = self.mask_index % len(batch)
             return batch[:m] + feats + batch[m:]

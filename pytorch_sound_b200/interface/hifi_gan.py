@@ -57,6 +57,7 @@ class MelSpectrogram(_PlanUser):
             wav = torch.nn.functional.pad(wav.unsqueeze(1), [self.pad_size, self.pad_size], mode='reflect').squeeze(1)
             idx = wav.device.index if wav.device.index is not None else torch.cuda.current_device()
             plan = _lib.cached_plan(idx, **self._center_kwargs)
+            self._fb_sync()
             if self._fb_dirty:
                 raise NotImplementedError("is_center=True with a state_dict-supplied mel_filter")
         else:

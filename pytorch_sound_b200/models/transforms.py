@@ -32,7 +32,13 @@ def _db_to_log(db: Optional[float]) -> Optional[float]:
 
 
 class _PlanUser(nn.Module):
-    """Shared plumbing: plan lookup per device, custom-filterbank handling after load_state_dict."""
+    """Shared plumbing: plan lookup per device, custom-filterbank handling.
+
+    The kernel applies the filterbank of its PLAN (device tables), not the registered torch buffer, so the buffer
+    is watched: whenever it is replaced or written in place (load_state_dict, `.copy_`, `.to`) — detected through
+    the tensor's identity and `_version` counter, two integer compares per call — it is compared with the default
+    filterbank of the geometry; a differing buffer gets a private plan carrying exactly those weights, and going
+    back to the default goes back to the shared plan."""
 
     _fb_buffer_name: Optional[str] = None
 
@@ -42,29 +48,42 @@ class _PlanUser(nn.Module):
         self._private_plans = {}
         self._fb_dirty = False
         self._fb_default: Optional[torch.Tensor] = None
+        self._fb_seen = None      # (id, _version) of the buffer the current _fb_dirty / private plans belong to
+        self._fb_owner = None     # patch.py hybrids: the reference module whose buffer is the one to watch
+
+    def _fb_tensor(self) -> Optional[torch.Tensor]:
+        """The registered filterbank as (n_mels, n_freq), or None for operators without one."""
+        if self._fb_buffer_name is None:
+            return None
+        owner = self._fb_owner() if self._fb_owner is not None else self
+        return getattr(owner, self._fb_buffer_name, None) if owner is not None else None
+
+    def _fb_sync(self) -> None:
+        fb = self._fb_tensor()
+        if fb is None or self._fb_default is None:
+            return
+        key = (id(fb), fb._version)
+        if key == self._fb_seen:
+            return
+        self._fb_seen = key
+        loaded = fb.detach().to('cpu', torch.float32)
+        self._fb_dirty = loaded.shape != self._fb_default.shape or not torch.equal(loaded, self._fb_default)
+        self._private_plans = {}
 
     def _plan(self, device: torch.device) -> "_lib.Plan":
         if device.type != 'cuda':
             raise RuntimeError(functional.NO_CPU_MSG)
         idx = device.index if device.index is not None else torch.cuda.current_device()
+        self._fb_sync()
         if not self._fb_dirty:
             return _lib.cached_plan(idx, **self._plan_kwargs)
-        # a state_dict replaced the filterbank: use a private plan carrying those weights
+        # the registered filterbank differs from the geometry's default: private plan carrying those weights
         pl = self._private_plans.get(idx)
         if pl is None:
             pl = _lib.Plan(_lib.make_config(**self._plan_kwargs), idx)
-            pl.set_filterbank(getattr(self, self._fb_buffer_name).detach().cpu().numpy())
+            pl.set_filterbank(self._fb_tensor().detach().to('cpu', torch.float32).contiguous().numpy())
             self._private_plans[idx] = pl
         return pl
-
-    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
-        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
-        name = self._fb_buffer_name
-        if name is not None and prefix + name in state_dict and self._fb_default is not None:
-            loaded = getattr(self, name).detach().cpu()
-            if loaded.shape != self._fb_default.shape or not torch.equal(loaded, self._fb_default):
-                self._fb_dirty = True
-                self._private_plans = {}
 
 
 class STFT(_PlanUser):
@@ -238,9 +257,34 @@ class LogMelSpectrogramTorchAudio(_PlanUser):
         self.melfunc.mel_scale = _Buffers()
         self.melfunc.spectrogram.register_buffer('window', torch.from_numpy(_lib.hann_window(win_length)))
         self.melfunc.mel_scale.register_buffer('fb', torch.from_numpy(fb.T.copy()))
+        self._fb_default = torch.from_numpy(fb).clone()
         self._plan_kwargs = dict(sample_rate=sr_even, n_fft=n_fft, win_length=win_length, hop_length=hop_length,
                                  n_mels=mel_size, fmin=mel_min, fmax=f_max, pad_mode=_lib.PAD_CENTER,
                                  mel_scale=_lib.MEL_HTK, mel_norm=_lib.NORM_NONE, power=2)
+
+    _fb_buffer_name = 'melfunc.mel_scale.fb'
+
+    def _fb_tensor(self) -> Optional[torch.Tensor]:
+        owner = self._fb_owner() if self._fb_owner is not None else self
+        try:
+            return owner.melfunc.mel_scale.fb.t()  # torchaudio keeps (n_freq, n_mels)
+        except AttributeError:
+            return None
+
+    def _fb_sync(self) -> None:
+        # `.t()` makes a new view object per call: key the watch on the underlying buffer instead
+        owner = self._fb_owner() if self._fb_owner is not None else self
+        try:
+            base = owner.melfunc.mel_scale.fb
+        except AttributeError:
+            return
+        key = (id(base), base._version)
+        if key == self._fb_seen:
+            return
+        self._fb_seen = key
+        loaded = base.detach().to('cpu', torch.float32).t()
+        self._fb_dirty = loaded.shape != self._fb_default.shape or not torch.equal(loaded, self._fb_default)
+        self._private_plans = {}
 
     def forward(self, wav: torch.Tensor, log_offset: float = 1e-6) -> torch.Tensor:
         epi = _lib.make_epilogue(_lib.LOG_LN_OFFSET, log_offset, self.min_db, self.max_db)

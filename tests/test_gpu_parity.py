@@ -310,23 +310,66 @@ def test_c2_full_size_properties(torch_cuda):
 
 def test_c1_pure_sine_vs_oracle(torch_cuda, golden):
     """BASELINE config C1 (1 x 22050 pure 440 Hz sine): an ill-conditioned input — most mel bands sit at the fp32
-    round-off floor of ANY fp32 transform (peak bin 128, far bins ~1e-6, then log(mel + 1e-6)).  The reference's
-    own two fp32 formulations differ by 1.6e-3 here (SURVEY 0.6) and its conv-DFT output is 5e-4 from float64;
-    an fp32 FFT (ours, and torch.stft's) carries ~8x the per-bin round-off of a direct DFT.  Judged with 5e-3;
-    the 1e-4 bar applies to the conditioned sine+noise inputs of SURVEY 8d (every other test in this file)."""
+    round-off floor of ANY fp32 transform (peak bin 128, far bins ~1e-6, then log(mel + 1e-6)).
+
+    The reference has two fp32 formulations of this path and both are recorded in the golden file (outputs of the
+    unmodified reference): the direct conv-DFT (`STFT`, 1024-term dot products) is 5.4e-4 from float64 on C1, its
+    FFT formulation (`STFTTorchAudio` = torch.stft, what Audio2Mel / the HiFi-GAN front-end run) is 2.0e-3 — an
+    fp32 FFT carries the round-off of log2(N) butterfly stages in every bin.  The kernel is an fp32 FFT, so its
+    bar on C1 is the reference's own FFT formulation: within 2x of that error (tools/c1_probe.py shows that the
+    approximate sqrt / log2 and the generated window contribute nothing measurable).  On the bands that carry the
+    signal (within 60 dB of the loudest) the 1e-4 bar holds on C1 too."""
     torch = torch_cuda
     from pytorch_sound_b200.models import transforms as T
 
     x = golden["c1.wav"]
     y = T.LogMelSpectrogram(**GEO).cuda()(cuda(torch, x)).cpu().numpy()
     ref = mo.log_mel_spectrogram(x, **GEO, clamp=False)
+    fb = mo.mel_filterbank(22050, 1024, 80, 0.0, 8000.0)
+    ref_fft = np.log(np.einsum("mf,bft->bmt", fb, golden["c1.stfta_mag"]).astype(np.float32) + np.float32(1e-6))
     err_kernel = mo.parity_error(y, ref)
-    err_reference = mo.parity_error(golden["c1.logmel"], ref)
-    print(f"C1 pure sine: kernel {err_kernel:.2e}, reference fp32 {err_reference:.2e}")
-    assert err_kernel < 5e-3
-    # where the signal is (mel bands within 60 dB of the loudest) the 1e-4 bar holds on C1 too
+    err_ref_conv = mo.parity_error(golden["c1.logmel"], ref)
+    err_ref_fft = mo.parity_error(ref_fft, ref)
+    print(f"C1 pure sine vs float64: kernel {err_kernel:.2e}, reference conv-DFT {err_ref_conv:.2e}, "
+          f"reference torch.stft {err_ref_fft:.2e}")
+    assert err_kernel <= 2.0 * err_ref_fft
     strong = ref > ref.max() - np.log(1e3)
     assert np.max(np.abs(y - ref)[strong] / np.maximum(1.0, np.abs(ref[strong]))) < TOL
+
+
+def test_spectrogram_masker_on_cuda(torch_cuda):
+    """SpectrogramMasker on CUDA tensors against the reference's formulation (models/transforms.py:408-416:
+    pad with win//2 ones on the left and zeros on the right, mean-filter conv of width win / stride hop, ceil),
+    for masks from pad_collate_fn (ones over the valid samples, data/dataset.py:73-74,230-250); `from_lengths`
+    and the frame mask the extractor writes in the same launch agree with it."""
+    torch = torch_cuda
+    F = torch.nn.functional
+    from pytorch_sound_b200.models import transforms as T
+
+    for win, hop, L, lens in [(1024, 256, 22050, [22050, 1, 700, 12345, 21800]), (800, 200, 6000, [6000, 4500, 5999, 399]),
+                              (2048, 512, 9000, [9000, 2047, 2048, 2049])]:
+        mask = torch.zeros(len(lens), L, device="cuda")
+        for i, n in enumerate(lens):
+            mask[i, :n] = 1
+        m = F.pad(F.pad(mask, [0, win // 2], value=0.), [win // 2, 0], value=1.)
+        ref = torch.ceil(F.conv1d(m.unsqueeze(1), torch.full((1, 1, win), 1.0 / win, device="cuda"), stride=hop).squeeze(1))
+        masker = T.SpectrogramMasker(win, hop)
+        got = masker(mask)
+        assert got.is_cuda and got.shape == ref.shape and torch.equal(got, ref)
+        lengths = torch.tensor(lens, device="cuda", dtype=torch.int32)
+        assert torch.equal(masker.from_lengths(lengths, L), ref)
+    # the extractor emits the same frame mask from `lengths` in its own launch (frame_mask=True)
+    lens = [22050, 15000, 300, 513]
+    x = torch.from_numpy(mo.synth_clips(4, 22050, 22050, seed=3)).cuda()
+    lengths = torch.tensor(lens, device="cuda", dtype=torch.int32)
+    for i, n in enumerate(lens):
+        x[i, n:] = 0
+    lm = T.LogMelSpectrogram(**GEO).cuda()
+    y, fmask = lm(x, lengths=lengths, frame_mask=True)
+    masker = T.SpectrogramMasker(1024, 256)
+    assert fmask.shape == (4, 87) and fmask.dtype == torch.float32
+    assert torch.equal(fmask, masker.from_lengths(lengths, 22050))
+    assert torch.equal(y, lm(x, lengths=lengths))
 
 
 def test_feature_loader_and_lengths_on_gpu(torch_cuda):

@@ -67,10 +67,34 @@ def test_state_dict_roundtrip_with_reference_keys(built_lib):
     sd["stft.forward_basis"] = torch.zeros(1026, 1, 1024)  # present in reference checkpoints
     sd["stft.inverse_basis"] = torch.zeros(1026, 1, 1024)
     lm.load_state_dict(sd)  # strict load must accept the reference's extra conv kernels
+    lm._fb_sync()
     assert not lm._fb_dirty
-    sd["mel_filter"] = sd["mel_filter"] * 2
+    default = sd["mel_filter"].clone()
+    sd["mel_filter"] = default * 2
     lm.load_state_dict(sd)
+    lm._fb_sync()
     assert lm._fb_dirty  # a different filterbank switches the module to a private plan
+    lm._private_plans[0] = object()  # stand-in for the plan a forward would have built
+    sd["mel_filter"] = default
+    lm.load_state_dict(sd)  # back to the default weights: the stale private plan must go
+    lm._fb_sync()
+    assert not lm._fb_dirty and lm._private_plans == {}
+    lm.mel_filter[3, 10] += 1.0  # in-place edit of the registered buffer is seen too
+    lm._fb_sync()
+    assert lm._fb_dirty
+    lm.mel_filter.copy_(default)
+    lm._fb_sync()
+    assert not lm._fb_dirty
+    # the torchaudio-named variant watches melfunc.mel_scale.fb (stored transposed, as torchaudio does)
+    ta = T.LogMelSpectrogramTorchAudio(22050, 80, 1024, 1024, 256, -50, 30)
+    ta._fb_sync()
+    assert not ta._fb_dirty
+    sd = {k: v.clone() for k, v in ta.state_dict().items()}
+    assert "melfunc.mel_scale.fb" in sd and sd["melfunc.mel_scale.fb"].shape == (513, 80)
+    sd["melfunc.mel_scale.fb"] = sd["melfunc.mel_scale.fb"] * 0.5
+    ta.load_state_dict(sd)
+    ta._fb_sync()
+    assert ta._fb_dirty and tuple(ta._fb_tensor().shape) == (80, 513)
 
 
 def test_cpu_tensors_raise_not_fallback(built_lib):
@@ -348,6 +372,79 @@ def test_banded_mel_schedule_reproduces_the_filterbank(built_lib, cfg):
     assert fn(Wd.ctypes.data, 9, Wd.shape[1], int(pair), dense.ctypes.data, info.ctypes.data) == 0
     np.testing.assert_array_equal(dense, Wd)
     assert info[4] == 0
+
+
+def test_patch_installs_hybrids_that_keep_the_reference_paths(monkeypatch, built_lib):
+    """patch() against a stand-in `pytorch_sound` whose classes ARE nn.Modules (like the real ones): what is installed
+    subclasses the reference class (so `inverse`, buffers and autograd survive), CPU / grad-requiring inputs run the
+    reference implementation, `settings.from_reference()` is applied, and unpatch() restores the originals."""
+    import sys
+    import types
+
+    import pytorch_sound_b200
+    from pytorch_sound_b200 import patch as P
+    from pytorch_sound_b200 import settings as S
+
+    for name in [m for m in sys.modules if m == "pytorch_sound" or m.startswith("pytorch_sound.")]:
+        monkeypatch.delitem(sys.modules, name)
+
+    class RefSTFT(torch.nn.Module):
+        def __init__(self, filter_length=1024, hop_length=512, win_length=None, window='hann'):
+            super().__init__()
+            self.register_buffer('forward_basis', torch.ones(3))
+            self.calls = 0
+
+        def transform(self, wav):
+            self.calls += 1
+            return wav * 2, wav * 3
+
+        def inverse(self, mag, phase):
+            return mag + phase
+
+    class RefLogMel(torch.nn.Module):
+        def __init__(self, sample_rate, mel_size, n_fft, win_length, hop_length, min_db=None, max_db=None,
+                     mel_min=0., mel_max=None):
+            super().__init__()
+            self.register_buffer('mel_filter', torch.zeros(mel_size, n_fft // 2 + 1))
+
+        def forward(self, wav, log_offset=1e-6):
+            return wav.sum() + log_offset
+
+    pkg = types.ModuleType("pytorch_sound")
+    models = types.ModuleType("pytorch_sound.models")
+    tr = types.ModuleType("pytorch_sound.models.transforms")
+    st = types.ModuleType("pytorch_sound.settings")
+    st.SAMPLE_RATE, st.MIN_DB, st.MAX_DB = 16000, -40, 20
+    tr.STFT, tr.LogMelSpectrogram = RefSTFT, RefLogMel
+    pkg.models, pkg.settings, models.transforms = models, st, tr
+    for m in (pkg, models, tr, st):
+        monkeypatch.setitem(sys.modules, m.__name__, m)
+    saved = {k: getattr(S, k) for k in ("SAMPLE_RATE", "MIN_DB", "MAX_DB")}
+    try:
+        assert pytorch_sound_b200.patch_pytorch_sound() is True
+        assert (S.SAMPLE_RATE, S.MIN_DB, S.MAX_DB) == (16000, -40, 20)  # live settings.py values are honoured
+        H = tr.STFT
+        assert issubclass(H, RefSTFT) and H is not RefSTFT and tr._reference_STFT is RefSTFT
+        m = H(filter_length=1024, hop_length=256)
+        assert set(m.state_dict()) == {"forward_basis"}  # the twin adds no keys
+        x = torch.ones(2, 4096)
+        mag, ph = m.transform(x)  # CPU tensor -> the reference implementation, not an error
+        assert m.calls == 1 and torch.equal(mag, x * 2) and torch.equal(m.inverse(mag, ph), x * 5)
+        xg = torch.ones(2, 4096, requires_grad=True)
+        m.transform(xg)
+        assert m.calls == 2  # needs grad -> reference (autograd) path
+        lm = tr.LogMelSpectrogram(22050, 80, 1024, 1024, 256)
+        assert float(lm(torch.ones(4))) == pytest.approx(4.0 + 1e-6)
+        assert lm._b200._fb_tensor() is lm.mel_filter  # the twin watches the hybrid's (reference-named) buffer
+        lm._b200._fb_sync()
+        assert lm._b200._fb_dirty  # this stand-in's all-zero filter differs from the geometry's default
+        P.patch()  # idempotent: the recorded originals are not overwritten by hybrids
+        assert tr._reference_STFT is RefSTFT and issubclass(tr.STFT, RefSTFT)
+        P.unpatch()
+        assert tr.STFT is RefSTFT and tr.LogMelSpectrogram is RefLogMel and not hasattr(tr, "_reference_STFT")
+    finally:
+        for k, v in saved.items():
+            setattr(S, k, v)
 
 
 def test_patch_swaps_operators_into_an_importable_pytorch_sound(monkeypatch):
