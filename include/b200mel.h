@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200MEL_VERSION 100 /* 0.1.0 */
+#define B200MEL_VERSION 200 /* 0.2.0 */
 
 /* error codes */
 #define B200MEL_OK 0
@@ -71,7 +71,8 @@ extern "C" {
 typedef struct b200mel_config {
     int32_t struct_size; /* = sizeof(b200mel_config), for forward compatibility */
     int32_t sample_rate;
-    int32_t n_fft;      /* supported: 1024, 2048 */
+    int32_t n_fft;      /* a power of two in [32, 2048]: sizes <= 1024 run the 1024-point pair kernel on the zero-extended
+                           frame (bin k of an N-point DFT is bin k * 1024 / N of its 1024-point DFT), 2048 the split kernel */
     int32_t win_length; /* <= n_fft; periodic Hann, centre-padded to n_fft (models/transforms.py:30-31) */
     int32_t hop_length;
     int32_t n_mels; /* 0 = spectrum-only plan (STFT / STFTTorchAudio) */
@@ -142,6 +143,27 @@ int b200mel_forward(const b200mel_plan *plan, const float *wav, int64_t B, int64
                     const int32_t *lengths, const b200mel_epilogue *epi, float *out_mel, int32_t spec_kind,
                     float *out_a, float *out_b, void *stream);
 
+/* Extensible form of b200mel_forward: every pointer of one call in a struct (struct_size guards the layout), plus
+ * the outputs added after version 100:
+ *   out_frame_mask  nullable device pointer float32 (B, T): frame-level validity mask with the semantics of
+ *                   SpectrogramMasker.forward (models/transforms.py:397-416) applied to the wave-level mask of ones
+ *                   that SpeechDataset appends (data/dataset.py:73-74,92-93): frame t is 1 iff its window
+ *                   [t*hop - win/2, t*hop + win/2) contains a valid sample or left padding, i.e.
+ *                   t*hop - win_length/2 < lengths[b] (all ones without `lengths`).  Written by the same launch
+ *                   as the mel frames (centre framing only).
+ * b200mel_forward(plan, wav, B, L, row_stride, lengths, epi, out_mel, spec_kind, out_a, out_b, stream) is exactly
+ * b200mel_forward_io with out_frame_mask = NULL. */
+typedef struct b200mel_io {
+    int32_t struct_size; /* = sizeof(b200mel_io) */
+    int32_t spec_kind;   /* B200MEL_SPEC_* */
+    const float *wav;
+    int64_t B, L, row_stride;
+    const int32_t *lengths;
+    float *out_mel, *out_a, *out_b;
+    float *out_frame_mask;
+} b200mel_io;
+int b200mel_forward_io(const b200mel_plan *plan, const b200mel_io *io, const b200mel_epilogue *epi, void *stream);
+
 /* Same, but wav_host / out_mel_host are HOST pointers (pinned memory gives
  * asynchronous copies): H2D copy -> kernel -> D2H copy on `stream` using
  * plan-owned device staging that grows on demand (so this entry point is NOT
@@ -161,7 +183,15 @@ int b200mel_forward_host(b200mel_plan *plan, const float *wav_host, int64_t B, i
  *                         device buffer of 2 doubles owned by the caller; two launches (moments, scale).
  * b200mel_mel_to_mfcc  <- models/transforms.py:419-430 MelToMFCC.forward: out (B, n_mfcc, T) =
  *                         dct (n_mfcc, n_mels) @ mel (B, n_mels, T); dct is a device pointer (the module's
- *                         `dct_mat` buffer, torchaudio.functional.create_dct transposed, :427). */
+ *                         `dct_mat` buffer, torchaudio.functional.create_dct transposed, :427).
+ * b200mel_stft_loss_terms <- models/sound.py:139-141, the two reductions of one resolution of multi_stft_loss over
+ *                         magnitude tensors (B, F, T) (n_per_clip = F * T, contiguous):
+ *                           out2[0] += mean_b ||t_b - p_b||_F / ||t_b||_F          (spectral convergence)
+ *                           out2[1] += mean_b sum |ln(t_b + eps) - ln(p_b + eps)| / n_per_clip
+ *                         out2 (device, 2 floats) ACCUMULATES so the resolutions of one loss add up in place (zero it
+ *                         first); scratch is a caller-owned device buffer of 3 * B doubles.  Memset + two launches. */
+int b200mel_stft_loss_terms(const float *pred_mag, const float *target_mag, int64_t B, int64_t n_per_clip, float eps,
+                            double *scratch, float *out2, void *stream);
 int b200mel_preemphasis(const float *x, int64_t B, int64_t L, int64_t x_row_stride, float coef, float *y,
                         int64_t y_row_stride, void *stream);
 int b200mel_volume_norm(const float *x, int64_t n, float target_db, float *y, double *scratch, void *stream);

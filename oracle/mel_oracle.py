@@ -299,6 +299,36 @@ def mel_to_mfcc(mel, n_mfcc, norm="ortho"):
     mel = np.asarray(mel, dtype=np.float64)
     return np.einsum("cm,bmt->bct", create_dct(n_mfcc, mel.shape[1], norm).T, mel)
 
+def multi_stft_loss(pred, target, stft_params, eps=1e-5):
+    """models/sound.py:120-147, float64.  stft_params: (n_fft, window size, hop size) triplets; every resolution runs
+    STFTTorchAudio(filter_length=win, hop_length=hop, win_length=win, n_fft=fft).transform (models/sound.py:113-117),
+    i.e. a Hann window of `win` samples centre-padded to n_fft (torch.stft), centre reflect padding of n_fft // 2.
+    Returns (loss, spectral-convergence loss, log-magnitude loss), each averaged over the resolutions."""
+    loss = sc = mg = 0.0
+    for fft, win, hop in stft_params:
+        p = np.abs(stft_complex(pred, fft, hop, win))
+        t = np.abs(stft_complex(target, fft, hop, win))
+        n = t.shape[1] * t.shape[2]
+        sc_ = np.mean(np.sqrt(np.sum((t - p) ** 2, axis=(1, 2))) / np.sqrt(np.sum(t ** 2, axis=(1, 2))))
+        mg_ = np.mean(np.sum(np.abs(np.log(t + eps) - np.log(p + eps)), axis=(1, 2))) / n
+        loss += sc_ + mg_
+        sc += sc_
+        mg += mg_
+    k = len(stft_params)
+    return loss / k, sc / k, mg / k
+
+
+def spectrogram_mask(wav_mask, win_length, hop_length):
+    """SpectrogramMasker.forward (models/transforms.py:408-416): pad win//2 zeros on the right and win//2 ones on the
+    left, mean-filter conv of width win / stride hop, ceil."""
+    m = np.asarray(wav_mask, dtype=np.float64)
+    half = win_length // 2
+    m = np.concatenate([np.ones(m.shape[:-1] + (half,)), m, np.zeros(m.shape[:-1] + (half,))], axis=-1)
+    T = (m.shape[-1] - win_length) // hop_length + 1
+    idx = np.arange(win_length)[None, :] + hop_length * np.arange(T)[:, None]
+    return np.ceil(m[..., idx].mean(axis=-1))
+
+
 # ---------------------------------------------------------------------------------------------
 class TorchReference:
     """The reference modules' op sequences on torch-CPU float32, with today's torch API

@@ -34,6 +34,14 @@ class Epilogue(C.Structure):
     ]
 
 
+class IO(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("spec_kind", C.c_int32), ("wav", C.c_void_p), ("B", C.c_int64), ("L", C.c_int64),
+        ("row_stride", C.c_int64), ("lengths", C.c_void_p), ("out_mel", C.c_void_p), ("out_a", C.c_void_p),
+        ("out_b", C.c_void_p), ("out_frame_mask", C.c_void_p),
+    ]
+
+
 # every symbol include/b200mel.h declares: (restype, argtypes)
 SYMBOLS = {
     "b200mel_version": (C.c_int, []),
@@ -47,12 +55,15 @@ SYMBOLS = {
     "b200mel_plan_destroy": (C.c_int, [C.c_void_p]),
     "b200mel_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                   C.POINTER(Epilogue), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200mel_forward_io": (C.c_int, [C.c_void_p, C.POINTER(IO), C.POINTER(Epilogue), C.c_void_p]),
     "b200mel_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.POINTER(Epilogue),
                                        C.c_void_p, C.c_void_p]),
     "b200mel_launch_count": (C.c_int64, []),
     "b200mel_preemphasis": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_int64,
                                       C.c_void_p]),
     "b200mel_volume_norm": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200mel_stft_loss_terms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
     "b200mel_mel_to_mfcc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
                                       C.c_void_p]),
 }

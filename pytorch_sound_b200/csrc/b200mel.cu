@@ -24,6 +24,7 @@
 #include "../../include/b200mel.h"
 #include "fft32.cuh"
 #include "logmel_kernel.cuh"
+#include "logmel_fast.cuh"
 #include "spec_kernel.cuh"
 #include "wave_ops.cuh"
 
@@ -106,11 +107,14 @@ struct b200mel_plan {
     b200mel_config cfg;
     int device;
     int num_sms;
-    int pad, n_freq;
-    bool pair;        // n_fft == 1024: two frames per complex FFT
+    int pad, n_freq;  // n_freq = logical n_fft / 2 + 1 (rows of the filterbank and of the spectrum outputs)
+    int phys_n_fft;   // transform the kernels run: 1024 for every power-of-two n_fft <= 1024, else 2048
+    int bin_step;     // phys_n_fft / n_fft: logical bin k is physical bin k * bin_step
+    int phys_n_freq;  // phys_n_fft / 2 + 1
+    bool pair;        // phys_n_fft == 1024: two frames per complex FFT
     int pair_frames;  // frames per task (2 in pair mode unless hop > n_fft, else 1)
     // device tables
-    float *d_window = nullptr;
+    float *d_window = nullptr, *d_window_t = nullptr;
     float2 *d_tw = nullptr, *d_tw_post = nullptr;
     MelEntry *d_mel_entries = nullptr;
     float *d_mel_w = nullptr;
@@ -140,14 +144,14 @@ static void free_mel_tables(b200mel_plan *pl) {
 
 // Shared-memory carve-up (must match logmel_kernel.cuh): tw | window | mel entries | mel weights | mbarriers | warp regions
 static int layout_smem(b200mel_plan *pl) {
-    const int n_fft = pl->cfg.n_fft;
+    const int n_fft = pl->phys_n_fft;
     const int span = n_fft + (pl->pair_frames == 2 ? pl->cfg.hop_length : 0);
     pl->stage_bytes = ((span + 8) * 4 + 15) & ~15;
     int region = kStageOff + pl->stage_bytes;
     if (region < kXposeBytes) region = kXposeBytes;
     pl->region_bytes = (region + 127) & ~127;
     pl->off_window = 32 * 32 * 8;
-    pl->off_entries = pl->off_window + n_fft * 4;
+    pl->off_entries = pl->off_window + std::max(n_fft * 4, 32 * 36 * 4);
     pl->off_melw = pl->off_entries + pl->mel_rounds * 32 * (int)sizeof(MelEntry);
     pl->off_bar = pl->off_melw + pl->mel_w_len * 4;
     pl->off_regions = (pl->off_bar + (kMaxWarps + 1) * 8 + 127) & ~127;  // per-warp mbarriers + the table mbarrier
@@ -167,7 +171,7 @@ static int layout_smem(b200mel_plan *pl) {
     pl->sp_off_slots = pl->sp_off_bar + kSpecWarps * 8;
     pl->sp_off_regions = (pl->sp_off_slots + kSpecWarps * (int)sizeof(SpecSlot) + 127) & ~127;
     pl->sp_off_tiles = pl->sp_off_regions + kSpecWarps * pl->region_bytes;
-    pl->sp_smem_bytes = pl->sp_off_tiles + 2 * pl->n_freq * (cols + 1) * 4;
+    pl->sp_smem_bytes = pl->sp_off_tiles + 2 * pl->phys_n_freq * (cols + 1) * 4;
     if (pl->sp_smem_bytes > kMaxSmem)
         return fail(B200MEL_EUNSUP, "plan: hop_length too large for the shared-memory staging of the spectrum kernel");
     return B200MEL_OK;
@@ -295,8 +299,18 @@ static int build_mel_schedule(bool pair, const float *W, int n_mels, int F, MelS
     return B200MEL_OK;
 }
 
-static int upload_filterbank(b200mel_plan *pl, const float *W, int n_mels, int F) {
+static int upload_filterbank(b200mel_plan *pl, const float *W_log, int n_mels, int F_log) {
     MelSchedule sch;
+    // logical bin k lives at physical bin k * bin_step of the transform the kernel runs
+    const int F = pl->phys_n_freq;
+    std::vector<float> W_phys;
+    const float *W = W_log;
+    if (pl->bin_step != 1) {
+        W_phys.assign((size_t)n_mels * F, 0.f);
+        for (int m = 0; m < n_mels; ++m)
+            for (int k = 0; k < F_log; ++k) W_phys[(size_t)m * F + (size_t)k * pl->bin_step] = W_log[(size_t)m * F_log + k];
+        W = W_phys.data();
+    }
     if (int rc = build_mel_schedule(pl->pair, W, n_mels, F, &sch)) return rc;
     pl->top_groups = sch.top_groups;
     for (int r = 0; r < kMaxMelRounds; ++r) pl->round_groups[r] = sch.round_groups[r], pl->round_wbase[r] = sch.round_wbase[r];
@@ -327,6 +341,36 @@ static kernel_fn pick_kernel(bool pair, int spec, bool mel, int power, int top_g
         case B200MEL_SPEC_RE_IM: return pair ? spec_kernel<true, 2> : spec_kernel<false, 2>;
         default: return pair ? spec_kernel<true, 3> : spec_kernel<false, 3>;
     }
+}
+
+// Fast-path instantiations (logmel_fast.cuh): {bins < 384, all bins} x round signatures of the filterbanks the
+// reference's defaults and the BASELINE configs produce.  A plan whose signature is not listed uses the generic kernel.
+struct FastEntry { int top; unsigned sig; int power; kernel_fn fn; };
+#define B200MEL_FAST(top, sig) {top, sig, 1, logmel_fast_kernel<top, sig, 1>}
+static const FastEntry g_fast[] = {
+    B200MEL_FAST(12, 0x731u),  // 22050 Hz / 1024 / 80 mels / 0-8000 Hz: settings.py, C2, C3, HiFi-GAN front-end
+    B200MEL_FAST(16, 0xa32u),  // 16000 Hz / 1024 / 80 mels / 0-8000 Hz: C5
+    B200MEL_FAST(16, 0xa42u),  // 22050 Hz / 1024 / 80 mels / 0-11025 Hz: Audio2Mel defaults (mel_fmax = None)
+};
+#undef B200MEL_FAST
+static unsigned plan_signature(const b200mel_plan *pl) {
+    if (pl->mel_rounds < 1 || pl->mel_rounds > 4) return 0;
+    unsigned sig = 0;
+    for (int r = 0; r < pl->mel_rounds; ++r) {
+        if (pl->round_groups[r] < 1 || pl->round_groups[r] > 15) return 0;
+        sig = (sig << 4) | (unsigned)pl->round_groups[r];
+    }
+    return sig;
+}
+static const bool g_no_fast = getenv("B200MEL_NO_FAST") != nullptr;  // A/B: always run the generic kernel
+static kernel_fn pick_fast_kernel(const b200mel_plan *pl) {
+    if (g_no_fast || !pl->pair || pl->pair_frames != 2 || pl->cfg.hop_length != kFastHop || pl->cfg.win_length != pl->phys_n_fft ||
+        pl->cfg.n_mels <= 0 || g_table_window || pl->n_warps != kMaxWarps)
+        return nullptr;
+    const unsigned sig = plan_signature(pl);
+    for (const FastEntry &e : g_fast)
+        if (e.top == pl->top_groups && e.sig == sig && e.power == pl->cfg.power) return e.fn;
+    return nullptr;
 }
 
 extern "C" {
@@ -399,8 +443,8 @@ int b200mel_plan_create(const b200mel_config *cfg, b200mel_plan **out) {
     if (!cfg || !out) return fail(B200MEL_EINVAL, "plan_create: null argument");
     if (cfg->struct_size != (int32_t)sizeof(b200mel_config))
         return fail(B200MEL_EINVAL, "plan_create: struct_size mismatch (ABI version skew)");
-    if (cfg->n_fft != 1024 && cfg->n_fft != 2048)
-        return fail(B200MEL_EUNSUP, "plan_create: n_fft must be 1024 or 2048 in this build");
+    if (cfg->n_fft < 32 || cfg->n_fft > 2048 || (cfg->n_fft & (cfg->n_fft - 1)))
+        return fail(B200MEL_EUNSUP, "plan_create: n_fft must be a power of two in [32, 2048] in this build");
     if (cfg->win_length <= 0 || cfg->win_length > cfg->n_fft)
         return fail(B200MEL_EINVAL, "plan_create: need 0 < win_length <= n_fft (models/transforms.py:28)");
     if (cfg->hop_length <= 0) return fail(B200MEL_EINVAL, "plan_create: hop_length must be positive");
@@ -431,15 +475,18 @@ int b200mel_plan_create(const b200mel_config *cfg, b200mel_plan **out) {
     pl->cfg = *cfg;
     pl->device = dev;
     pl->num_sms = prop.multiProcessorCount;
-    pl->pair = cfg->n_fft == 1024;
-    pl->pair_frames = (pl->pair && cfg->hop_length <= cfg->n_fft) ? 2 : 1;
+    pl->phys_n_fft = cfg->n_fft <= 1024 ? 1024 : 2048;
+    pl->bin_step = pl->phys_n_fft / cfg->n_fft;
+    pl->phys_n_freq = pl->phys_n_fft / 2 + 1;
+    pl->pair = pl->phys_n_fft == 1024;
+    pl->pair_frames = (pl->pair && cfg->hop_length <= pl->phys_n_fft) ? 2 : 1;
     pl->n_freq = cfg->n_fft / 2 + 1;
     pl->pad = cfg->pad_mode == B200MEL_PAD_CENTER ? cfg->n_fft / 2 : (cfg->n_fft - cfg->hop_length) / 2;
     if (pl->pad < 0) pl->pad = 0;
 
-    const int N = cfg->n_fft;
-    std::vector<float> win(N);
-    build_window(cfg->win_length, N, win.data());
+    const int N = pl->phys_n_fft;
+    std::vector<float> win(N, 0.f);  // logical window (centre-padded to n_fft), zero-extended to the physical transform
+    build_window(cfg->win_length, cfg->n_fft, win.data());
     for (auto &w : win) w *= 0.5f;  // exact; the separation pass omits its 1/2
     std::vector<float2> tw(32 * 32), twp(32);
     const double two_pi = 6.283185307179586476925286766559;
@@ -458,12 +505,19 @@ int b200mel_plan_create(const b200mel_config *cfg, b200mel_plan **out) {
         if ((e = cudaMalloc(&pl->d_tw, tw.size() * sizeof(float2))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc"); break; }
         if ((e = cudaMalloc(&pl->d_tw_post, twp.size() * sizeof(float2))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc"); break; }
         cudaMemcpy(pl->d_window, win.data(), N * sizeof(float), cudaMemcpyHostToDevice);
+        if (N == 1024) {  // lane-major copy: row l = w[32 j + l], j = 0..31, rows 36 floats apart
+            std::vector<float> wt(32 * 36, 0.f);
+            for (int l = 0; l < 32; ++l)
+                for (int j = 0; j < 32; ++j) wt[l * 36 + j] = win[32 * j + l];
+            if ((e = cudaMalloc(&pl->d_window_t, wt.size() * sizeof(float))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc"); break; }
+            cudaMemcpy(pl->d_window_t, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice);
+        }
         cudaMemcpy(pl->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice);
         e = cudaMemcpy(pl->d_tw_post, twp.data(), twp.size() * sizeof(float2), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpy(tables)"); break; }
         if (cfg->n_mels > 0) {
             std::vector<float> W((size_t)cfg->n_mels * pl->n_freq);
-            build_filterbank(cfg->sample_rate, N, cfg->n_mels, cfg->fmin, fmax, cfg->mel_scale == B200MEL_MEL_HTK,
+            build_filterbank(cfg->sample_rate, cfg->n_fft, cfg->n_mels, cfg->fmin, fmax, cfg->mel_scale == B200MEL_MEL_HTK,
                              cfg->mel_norm == B200MEL_NORM_SLANEY, W.data());
             rc = upload_filterbank(pl, W.data(), cfg->n_mels, pl->n_freq);
             if (rc) break;
@@ -476,6 +530,8 @@ int b200mel_plan_create(const b200mel_config *cfg, b200mel_plan **out) {
                     e = cudaFuncSetAttribute(pick_kernel(pl->pair, spec, spec == 0, power, top),
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
             }
+        for (const FastEntry &fe : g_fast)
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(fe.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute (is the library built for this GPU?)"); break; }
     } while (0);
     if (rc) {
@@ -502,6 +558,7 @@ int b200mel_plan_set_filterbank(b200mel_plan *plan, const float *weights, int32_
 int b200mel_plan_destroy(b200mel_plan *pl) {
     if (!pl) return B200MEL_OK;
     cudaFree(pl->d_window);
+    cudaFree(pl->d_window_t);
     cudaFree(pl->d_tw);
     cudaFree(pl->d_tw_post);
     free_mel_tables(pl);
@@ -514,7 +571,26 @@ int b200mel_plan_destroy(b200mel_plan *pl) {
 int b200mel_forward(const b200mel_plan *pl, const float *wav, int64_t B, int64_t L, int64_t row_stride,
                     const int32_t *lengths, const b200mel_epilogue *epi, float *out_mel, int32_t spec_kind,
                     float *out_a, float *out_b, void *stream) {
+    b200mel_io io;
+    memset(&io, 0, sizeof(io));
+    io.struct_size = (int32_t)sizeof(io);
+    io.spec_kind = spec_kind;
+    io.wav = wav, io.B = B, io.L = L, io.row_stride = row_stride, io.lengths = lengths;
+    io.out_mel = out_mel, io.out_a = out_a, io.out_b = out_b;
+    return b200mel_forward_io(pl, &io, epi, stream);
+}
+
+int b200mel_forward_io(const b200mel_plan *pl, const b200mel_io *io, const b200mel_epilogue *epi, void *stream) {
     if (!pl) return fail(B200MEL_EINVAL, "forward: null plan");
+    if (!io || io->struct_size != (int32_t)sizeof(b200mel_io)) return fail(B200MEL_EINVAL, "forward: io struct_size mismatch");
+    const float *wav = io->wav;
+    const int64_t B = io->B, L = io->L, row_stride = io->row_stride;
+    const int32_t *lengths = io->lengths;
+    float *out_mel = io->out_mel, *out_a = io->out_a, *out_b = io->out_b;
+    const int32_t spec_kind = io->spec_kind;
+    if (io->out_frame_mask && pl->cfg.pad_mode != B200MEL_PAD_CENTER)
+        return fail(B200MEL_EINVAL, "forward: out_frame_mask needs centre framing (SpectrogramMasker geometry)");
+    if (io->out_frame_mask && !out_mel) return fail(B200MEL_EINVAL, "forward: out_frame_mask is written by the mel launch");
     if (B < 0 || L < 0) return fail(B200MEL_EINVAL, "forward: negative shape");
     if (B > 0x7fffffff) return fail(B200MEL_EINVAL, "forward: more than 2^31 - 1 clips");
     if (B == 0) return B200MEL_OK;
@@ -544,6 +620,11 @@ int b200mel_forward(const b200mel_plan *pl, const float *wav, int64_t B, int64_t
     KParams p;
     memset(&p, 0, sizeof(p));
     p.wav = wav;
+    {
+        const uintptr_t lo = reinterpret_cast<uintptr_t>(wav), hi = reinterpret_cast<uintptr_t>(wav + (B - 1) * row_stride + L);
+        p.wav_lo16 = (unsigned long long)((lo + 15) & ~(uintptr_t)15);
+        p.wav_hi16 = (unsigned long long)(hi & ~(uintptr_t)15);
+    }
     p.row_stride = row_stride;
     p.B = B;
     p.L = (int)L;
@@ -551,16 +632,20 @@ int b200mel_forward(const b200mel_plan *pl, const float *wav, int64_t B, int64_t
     p.T = (int)T;
     p.hop = pl->cfg.hop_length;
     p.pad = pl->pad;
-    p.n_fft = pl->cfg.n_fft;
+    p.n_fft = pl->phys_n_fft;
+    p.n_fft_log = pl->cfg.n_fft;
+    p.bin_step = pl->bin_step;
+    p.n_freq_out = pl->n_freq;
     p.pair_frames = pl->pair_frames;
-    p.hann_full = (pl->pair && pl->cfg.win_length == pl->cfg.n_fft && !g_table_window) ? 1 : 0;
+    p.hann_full = (pl->pair && pl->cfg.win_length == pl->phys_n_fft && !g_table_window) ? 1 : 0;
     p.window = pl->d_window;
+    p.window_t = pl->d_window_t;
     p.tw = pl->d_tw;
     p.tw_post = pl->d_tw_post;
     p.mel_entries = pl->d_mel_entries;
     p.mel_w = pl->d_mel_w;
     p.n_mels = pl->cfg.n_mels;
-    p.n_freq = pl->n_freq;
+    p.n_freq = pl->phys_n_freq;
     p.mel_rounds = pl->mel_rounds;
     p.mel_w_len = pl->mel_w_len;
     for (int r = 0; r < kMaxMelRounds; ++r) p.round_groups[r] = pl->round_groups[r], p.round_wbase[r] = pl->round_wbase[r];
@@ -572,6 +657,8 @@ int b200mel_forward(const b200mel_plan *pl, const float *wav, int64_t B, int64_t
     p.region_bytes = pl->region_bytes;
     p.stage_bytes = pl->stage_bytes;
     p.out_mel = out_mel;
+    p.out_fmask = io->out_frame_mask;
+    p.win_half = pl->cfg.win_length / 2;
     p.out_a = out_a;
     p.out_b = out_b;
     p.mag_eps = pl->cfg.mag_eps;
@@ -619,7 +706,9 @@ int b200mel_forward(const b200mel_plan *pl, const float *wav, int64_t B, int64_t
     if (out_mel) {
         cfg.gridDim = dim3((unsigned)n_cta);
         cfg.blockDim = dim3(pl->n_warps * 32);
-        le = cudaLaunchKernelEx(&cfg, pick_kernel(pl->pair, 0, true, pl->cfg.power, pl->top_groups), p);
+        kernel_fn fn = (!lengths && p.use_log && !p.out_fmask) ? pick_fast_kernel(pl) : nullptr;
+        if (!fn) fn = pick_kernel(pl->pair, 0, true, pl->cfg.power, pl->top_groups);
+        le = cudaLaunchKernelEx(&cfg, fn, p);
         g_launches.fetch_add(1);
     }
     if (spec_kind && le == cudaSuccess) {
@@ -732,6 +821,28 @@ int b200mel_volume_norm(const float *x, int64_t n, float target_db, float *y, do
     g_launches.fetch_add(2);
     e = cudaGetLastError();
     return e == cudaSuccess ? B200MEL_OK : cuda_fail(e, "volume_norm launch");
+}
+
+int b200mel_stft_loss_terms(const float *pred_mag, const float *target_mag, int64_t B, int64_t n_per_clip, float eps,
+                            double *scratch, float *out2, void *stream) {
+    if (B < 0 || n_per_clip < 0) return fail(B200MEL_EINVAL, "stft_loss_terms: negative shape");
+    if (B == 0 || n_per_clip == 0) return fail(B200MEL_EINVAL, "stft_loss_terms: empty input (the reference divides by zero)");
+    if (!pred_mag || !target_mag || !scratch || !out2) return fail(B200MEL_EINVAL, "stft_loss_terms: null pointer");
+    int sms = 0;
+    if (int rc = current_sms(&sms)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)B * 3 * sizeof(double), st);
+    if (e != cudaSuccess) return cuda_fail(e, "stft_loss_terms memset");
+    // a few waves of CTAs over (chunks, clips)
+    long long by = B < 65535 ? B : 65535;
+    long long bx = (n_per_clip + 256 * 8 - 1) / (256 * 8);
+    const long long cap = std::max<long long>(1, (long long)sms * 8 / by);
+    if (bx > cap) bx = cap;
+    stft_loss_partial_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, st>>>(pred_mag, target_mag, B, n_per_clip, eps, scratch);
+    stft_loss_final_kernel<<<1, 32, 0, st>>>(scratch, B, n_per_clip, out2);
+    g_launches.fetch_add(2);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? B200MEL_OK : cuda_fail(e, "stft_loss_terms launch");
 }
 
 int b200mel_mel_to_mfcc(const float *mel, const float *dct, int64_t B, int32_t n_mels, int32_t n_mfcc, int64_t T,

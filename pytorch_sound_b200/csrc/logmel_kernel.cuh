@@ -75,15 +75,26 @@ struct MelEntry {  // one filterbank row as seen by one lane in one round; 8 byt
 
 struct KParams {
     const float *wav;
+    // first / last 16-byte boundary INSIDE the caller's tensor [wav, wav + (B-1) row_stride + L): bulk copies are
+    // widened to 16-byte boundaries but never leave this range (the <= 3 floats cut off at a misaligned tensor
+    // edge are fetched by the halo patch instead)
+    unsigned long long wav_lo16, wav_hi16;
     long long row_stride;
     long long B;
     int L;
     const int *lengths;
-    int T, hop, pad, n_fft;
+    int T, hop, pad;
+    int n_fft;        // PHYSICAL transform size the kernel runs: 1024 (pair) or 2048 (split)
+    int n_fft_log;    // logical n_fft of the plan: a power of two <= n_fft.  A 1024 / r-point DFT is bin r k of the
+                      // 1024-point DFT of the zero-extended frame, so smaller transforms run the same kernel with a
+                      // window table that is zero beyond n_fft_log samples, and use every r-th bin
+    int bin_step;     // r = n_fft / n_fft_log
+    int n_freq_out;   // n_fft_log / 2 + 1: rows of the spectrum outputs
     int pair_frames;  // frames per task: 2 (pair mode) or 1 (split mode, or pair mode with hop > n_fft)
     int hann_full;    // 1: win_length == n_fft, the kernel may generate the periodic Hann instead of reading the table
     // global copies of the CTA tables
     const float *window;    // [n_fft], periodic Hann centre-padded, pre-scaled by 0.5
+    const float *window_t;  // [32][36] lane-major copy of the same table (experimental fast-path variant)
     const float2 *tw;       // [16][32][2]  tw[((j >> 1) * 32 + lane) * 2 + (j & 1)] = exp(-2 pi i j lane / 1024)
     const float2 *tw_post;  // [32]      exp(-2 pi i lane / 2048)            (split mode)
     const MelEntry *mel_entries;  // [rounds][32]
@@ -95,6 +106,8 @@ struct KParams {
     int off_window, off_entries, off_melw, off_bar, off_regions, region_bytes, stage_bytes;
     // outputs
     float *out_mel, *out_a, *out_b;
+    float *out_fmask;  // nullable (B, T): SpectrogramMasker frame mask, 1 iff t * hop - win_half < clip length
+    int win_half;
     long long *dbg;  // phase-timing accumulators (debug builds only)
 #ifdef B200MEL_X_MELLITE_LDC
     float xw[64];    // probe: weights read from the kernel-parameter constant bank
@@ -179,6 +192,20 @@ __device__ __forceinline__ float2 magnitude2(float2 u, float2 v, float eps) {
     return make_float2(sqrt_approx(sq.x), sqrt_approx(sq.y));
 }
 
+// Pair-mode separation and magnitudes of one bin in four packed instructions (+ the two square roots):
+//   E = A + conj(B) is frame t, D = A - conj(B) has |D| = |frame t+1| (the -i rotation is never formed);
+//   {E.x, D.x} = {A.x, A.x} + {B.x, -B.x},  {E.y, D.y} = {A.y, A.y} + {-B.y, B.y},
+//   {|E|^2, |D|^2} = {E.x, D.x}^2 + {E.y, D.y}^2  — the same roundings as the scalar form x*x + (y*y).
+template <int kPower>
+__device__ __forceinline__ float2 pair_magnitudes(float2 A, float2 Bv, float eps) {
+    const float2 px = __fadd2_rn(make_float2(A.x, A.x), make_float2(Bv.x, -Bv.x));
+    const float2 py = __fadd2_rn(make_float2(A.y, A.y), make_float2(-Bv.y, Bv.y));
+    float2 sq = __ffma2_rn(px, px, __fmul2_rn(py, py));
+    if constexpr (kPower == 2) return sq;
+    sq = __fadd2_rn(sq, make_float2(eps, eps));
+    return make_float2(sqrt_approx(sq.x), sqrt_approx(sq.y));
+}
+
 template <int kPower>
 __device__ __forceinline__ float magnitude(float re, float im, float eps) {
     const float sq = fmaf(re, re, im * im);
@@ -186,7 +213,66 @@ __device__ __forceinline__ float magnitude(float re, float im, float eps) {
     return sqrt_approx(sq + eps);
 }
 
-// Everything that locates a task; recomputed identically by the prefetch and the consume side.
+// Geometry of the ONE bulk copy that stages a task's samples, computed identically by the request side and the
+// halo patch.  Padded-coordinate sample s of the span [s_first, s_first + span) sits at stage[s - s_first + delta];
+// delta in 0..3 makes stage and global address 16-byte congruent, as cp.async.bulk requires.  The copy covers the
+// in-range samples [max(s_first, 0), min(s_first + span, Li)) widened to 16-byte boundaries on both sides — the
+// extra <= 3 floats per side are neighbouring samples of the same tensor, never read as data — and is clamped to
+// the tensor: when a widened end would leave [wav_lo16, wav_hi16) (first / last row of a tensor whose ends are
+// not 16-byte aligned) that end moves inwards by 16 bytes and the samples it drops are marked uncovered.
+struct CopyGeom {
+    int c_lo, c_hi;        // padded-coordinate samples [c_lo, c_hi) are valid in the stage once the copy has landed
+    int delta;
+    int dst;               // stage index (floats) the copy starts at, a multiple of 4
+    uint32_t bytes;        // multiple of 16; 0 = nothing to copy
+    const void *src;       // 16-byte aligned global address
+    bool patch;            // part of the span is not covered by the copy: reflect halo and / or clamped floats
+};
+__device__ __forceinline__ CopyGeom copy_geom(const KParams &p, long long b, int s_first, int span, int Li) {
+    CopyGeom g;
+    const int p_lo = max(s_first, 0), p_hi = min(s_first + span, Li);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p.wav + b * p.row_stride + p_lo);
+    const int mis = (int)(a >> 2) & 3;     // floats by which the first in-range sample misses a 16-byte boundary
+    const int off = p_lo - s_first;        // its position in the span
+    g.delta = (mis - off) & 3;
+    uintptr_t a16 = a - 4 * (uintptr_t)mis;
+    uintptr_t e16 = (a + 4 * (uintptr_t)(p_hi - p_lo) + 15) & ~(uintptr_t)15;
+    g.c_lo = p_lo, g.c_hi = p_hi;
+    g.dst = off + g.delta - mis;
+    if (a16 < p.wav_lo16) a16 += 16, g.dst += 4, g.c_lo = p_lo + 4 - mis;
+    if (e16 > p.wav_hi16) e16 -= 16, g.c_hi = p_lo + (int)((e16 - a) >> 2);
+    g.src = reinterpret_cast<const void *>(a16);
+    g.bytes = e16 > a16 ? (uint32_t)(e16 - a16) : 0u;
+    if (g.bytes == 0u) g.c_hi = g.c_lo;
+    g.patch = s_first < g.c_lo || s_first + span > g.c_hi;
+    return g;
+}
+// Fill what the bulk copy did not cover, after it has landed: the reflected halo of an edge task (<= 4 of 44
+// tasks per 1-s clip) and the floats dropped by the tensor-edge clamp.  The source sample is almost always
+// inside the staged part, so it is copied within shared memory; only a reflection that leaves the staged span
+// (or a clamped float) falls back to global memory.
+__device__ __forceinline__ void patch_stage(const KParams &p, long long b, int s_first, int span, int Li,
+                                            const CopyGeom &g, float *stage, int lane) {
+    const float *row = p.wav + b * p.row_stride;
+    float *st = stage + g.delta - s_first;  // st[s] = sample at padded-coordinate position s
+    for (int s = s_first + lane; s < g.c_lo; s += 32) {
+        const int r = reflect_index(s, Li);
+        st[s] = (r >= g.c_lo && r < g.c_hi) ? st[r] : __ldg(row + r);
+    }
+    for (int s = g.c_hi + lane; s < s_first + span; s += 32) {
+        const int r = reflect_index(s, Li);
+        st[s] = (r >= g.c_lo && r < g.c_hi) ? st[r] : __ldg(row + r);
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void issue_copy(const CopyGeom &g, uint32_t stage_s, uint32_t bar) {
+    fence_proxy_async();
+    mbar_arrive_expect_tx(bar, g.bytes);  // bytes may be 0: the arrive alone completes the phase
+    if (g.bytes) tma_load_1d(stage_s + (uint32_t)(g.dst * 4), g.src, g.bytes, bar);
+}
+
+// Everything that locates a task of the spectrum kernel (spec_kernel.cuh); recomputed identically by the prefetch
+// and the consume side.
 struct Task {
     long long b;
     int t0, Li, s_first;  // first frame, clip length, first padded-coordinate sample of the span
@@ -199,38 +285,13 @@ __device__ __forceinline__ Task decode_task(const KParams &p, long long b, int q
     Task t;
     t.b = b;
     t.Li = p.lengths ? min(__ldg(p.lengths + b), p.L) : p.L;
-    const int Ti = p.lengths ? min(frames_of(t.Li, p.n_fft, p.hop, p.pad), p.T) : p.T;
+    const int Ti = p.lengths ? min(frames_of(t.Li, p.n_fft_log, p.hop, p.pad), p.T) : p.T;
     t.t0 = q * p.pair_frames;
     t.valid0 = t.t0 < Ti;
     t.valid1 = kPair && p.pair_frames == 2 && (t.t0 + 1 < Ti);
     t.s_first = t.t0 * p.hop - p.pad;
     t.span = p.n_fft + (t.valid1 ? p.hop : 0);
     return t;
-}
-
-// Stage index of padded-coordinate sample position `s` is (s - s_first + delta): delta in 0..3 makes the first
-// in-range sample land 16-byte-congruent with its global address, as the bulk copy requires.
-__device__ __forceinline__ int stage_delta(const float *row, const Task &t) {
-    const int p_lo = max(t.s_first, 0);
-    return (int)(((reinterpret_cast<uintptr_t>(row + p_lo) >> 2) - (uintptr_t)(p_lo - t.s_first)) & 3);
-}
-
-// One elected lane: arm the warp's mbarrier and issue the bulk copy of the in-range part of the span.
-// The copy is widened to 16-byte boundaries on both sides (the extra <= 3 floats on each side are never read
-// as samples: interior tasks ignore them, edge tasks overwrite the halo after the copy has landed).
-template <bool kPair>
-__device__ __forceinline__ void issue_stage(const KParams &p, const Task &t, float *stage, uint32_t bar) {
-    const float *row = p.wav + t.b * p.row_stride;
-    const int p_lo = max(t.s_first, 0), p_hi = min(t.s_first + t.span, t.Li);
-    const uintptr_t a = reinterpret_cast<uintptr_t>(row + p_lo), e = reinterpret_cast<uintptr_t>(row + p_hi);
-    const uintptr_t a16 = a & ~(uintptr_t)15, e16 = (e + 15) & ~(uintptr_t)15;
-    const int delta = stage_delta(row, t);
-    const int idx_lo = p_lo - t.s_first + delta;              // stage index of sample p_lo
-    float *dst = stage + (idx_lo - (int)((a >> 2) & 3));      // multiple of 4 floats by construction
-    const uint32_t bytes = (uint32_t)(e16 - a16);
-    fence_proxy_async();
-    mbar_arrive_expect_tx(bar, bytes);
-    tma_load_1d(smem_u32(dst), reinterpret_cast<const void *>(a16), bytes, bar);
 }
 
 // One mel round for one lane, G float4 weight groups, straight-line: all 3G 128-bit loads are issued before the
@@ -330,14 +391,12 @@ struct Desc {
     int b, t0;        // clip, first frame
     int delta;        // stage shift: sample s of the span sits at stage[s - s_first + delta]
     int Li;           // clip length (p.L unless `lengths`)
-    unsigned flags;   // 1: frame t0 exists, 2: frame t0+1 exists (pair mode), 4: span leaves [0, Li) (reflect patch)
+    unsigned flags;   // 1: frame t0 exists, 2: frame t0+1 exists (pair mode), 4: part of the span needs the patch
 };
 
-// Locate a task and (one elected lane) request its samples: arm the warp's mbarrier and issue ONE bulk copy of
-// the in-range part of the span, widened to 16-byte boundaries on both sides (the extra <= 3 floats per side
-// are never read as samples: interior tasks ignore them, edge tasks overwrite the halo after the copy landed).
-// Everything is computed uniformly by all lanes in straight-line code, so the scheduler can sink it into the
-// shadow of the surrounding FFT arithmetic; only the three PTX instructions at the end are predicated.
+// Locate a task and (one elected lane) request its samples: arm the warp's mbarrier and issue ONE bulk copy
+// (copy_geom).  Everything is computed uniformly by all lanes in straight-line code, so the scheduler can sink it
+// into the shadow of the surrounding FFT arithmetic; only the PTX instructions at the end are predicated.
 template <bool kPair>
 __device__ __forceinline__ Desc request_task(const KParams &p, int b, int q, int lane, uint32_t stage_s, uint32_t bar) {
     Desc d;
@@ -345,48 +404,24 @@ __device__ __forceinline__ Desc request_task(const KParams &p, int b, int q, int
     int Li = p.L, Ti = p.T;
     if (p.lengths) {
         Li = min(__ldg(p.lengths + b), p.L);
-        Ti = min(frames_of(Li, p.n_fft, p.hop, p.pad), p.T);
+        Ti = min(frames_of(Li, p.n_fft_log, p.hop, p.pad), p.T);
     }
     d.Li = Li;
     d.t0 = q * p.pair_frames;
     const bool v0 = d.t0 < Ti, v1 = kPair && p.pair_frames == 2 && d.t0 + 1 < Ti;
     const int s_first = d.t0 * p.hop - p.pad;
     const int span = p.n_fft + (v1 ? p.hop : 0);
-    const int p_lo = max(s_first, 0), p_hi = min(s_first + span, Li);
-    const uintptr_t src = reinterpret_cast<uintptr_t>(p.wav + (long long)b * p.row_stride + p_lo);
-    const int mis = (int)(src >> 2) & 3;   // floats by which the first in-range sample misses a 16-byte boundary
-    const int off = p_lo - s_first;        // its position in the span
-    d.delta = (mis - off) & 3;             // shift that makes stage and global address 16-byte congruent
-    d.flags = (v0 ? 1u : 0u) | (v1 ? 2u : 0u) | ((s_first < 0 || s_first + span > Li) ? 4u : 0u);
-    if (v0 && lane == 0) {
-        const uint32_t bytes = (uint32_t)(((p_hi - p_lo + mis) * 4 + 15) & ~15);
-#ifndef B200MEL_X_NOFENCE  // probe: cost of the proxy fence (unsafe)
-        fence_proxy_async();
-#endif
-        mbar_arrive_expect_tx(bar, bytes);
-        tma_load_1d(stage_s + (uint32_t)((off + d.delta - mis) * 4), reinterpret_cast<const void *>(src - 4 * mis), bytes, bar);
-    }
+    const CopyGeom g = copy_geom(p, b, s_first, span, Li);
+    d.delta = g.delta;
+    d.flags = (v0 ? 1u : 0u) | (v1 ? 2u : 0u) | (g.patch ? 4u : 0u);
+    if (v0 && lane == 0) issue_copy(g, stage_s, bar);
     return d;
 }
 
-// Reflected halo of an edge task (<= 4 of 44 tasks per 1-s clip): the out-of-range part of the span is filled
-// after the bulk copy has landed.  The reflected samples are almost always inside the staged in-range part, so
-// they are copied within shared memory; only a reflection that leaves the span falls back to global memory.
 __device__ __forceinline__ void patch_halo_smem(const KParams &p, const Desc &d, float *stage, int lane) {
     const int s_first = d.t0 * p.hop - p.pad;
     const int span = p.n_fft + ((d.flags & 2u) ? p.hop : 0);
-    const int p_lo = max(s_first, 0), p_hi = min(s_first + span, d.Li);
-    const float *row = p.wav + (long long)d.b * p.row_stride;
-    float *st = stage + d.delta - s_first;  // st[s] = sample at padded-coordinate position s
-    for (int s = s_first + lane; s < 0; s += 32) {
-        const int r = reflect_index(s, d.Li);
-        st[s] = (r >= p_lo && r < p_hi) ? st[r] : __ldg(row + r);
-    }
-    for (int s = d.Li + lane; s < s_first + span; s += 32) {
-        const int r = reflect_index(s, d.Li);
-        st[s] = (r >= p_lo && r < p_hi) ? st[r] : __ldg(row + r);
-    }
-    __syncwarp();
+    patch_stage(p, d.b, s_first, span, d.Li, copy_geom(p, d.b, s_first, span, d.Li), stage, lane);
 }
 
 // Pair mode, stage -> registers with the window applied: a[j] = {x_t[32 j + lane], x_t+1[32 j + lane]} * w[32 j + lane].
@@ -560,6 +595,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
         if (cq >= p.tasks_per_clip) cq -= p.tasks_per_clip, ++cb;
         const bool valid0 = d.flags & 1u, valid1 = d.flags & 2u;
         float2 a[32];
+        if (p.out_fmask && lane < p.pair_frames && d.t0 + lane < p.T)  // frame mask of this task's frames (models/transforms.py:397-416)
+            p.out_fmask[(long long)d.b * p.T + d.t0 + lane] = ((d.t0 + lane) * p.hop - p.win_half < d.Li) ? 1.f : 0.f;
 
         if (valid0) {
             PHASE_MARK(1);  // decode
@@ -635,12 +672,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
                 const int k = lane + 32 * k2;
                 // E = A + conj(B), D = A - conj(B) (the 1/2 is folded into the window): frame t is E, frame t+1 is
                 // O = -i D, and |O| = |D|, so the rotation is never formed.  conj() is an operand sign pattern.
-                const float2 Bc = make_float2(Bv.x, -Bv.y);
-                const float2 E = __fadd2_rn(A, Bc);
-                const float2 D = __fadd2_rn(A, make_float2(-Bc.x, -Bc.y));
                 if constexpr (kPair) {
-                    tile2[k] = magnitude2<kPower>(E, D, p.mag_eps);
+                    tile2[k] = pair_magnitudes<kPower>(A, Bv, p.mag_eps);
                 } else {
+                    const float2 Bc = make_float2(Bv.x, -Bv.y);
+                    const float2 E = __fadd2_rn(A, Bc);
+                    const float2 D = __fadd2_rn(A, make_float2(-Bc.x, -Bc.y));
                     // X[k] = E + W_2048^k O,  X[1024-k] = conj(E - W_2048^k O),  O = -i D,  W_2048^k = wl * W_64^{k2}
                     // -> P = D * (-i wl W_64^{k2})
                     constexpr float w64c = TwConst::c64[k2], w64s = TwConst::s64[k2];

@@ -90,9 +90,10 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) spec_kernel(const KParams 
     for (int i = tid; i < p.n_fft / 4; i += blockDim.x)
         reinterpret_cast<int4 *>(s_win)[i] = __ldg(reinterpret_cast<const int4 *>(p.window) + i);
     asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: caller memory is only touched below this line
+    const uint32_t stage_s = smem_u32(stage);
     if (lane == 0 && task < p.n_tasks) {
         const Task t = decode_task<kPair>(p, cb, cq);
-        if (t.valid0) issue_stage<kPair>(p, t, stage, bar);
+        if (t.valid0) issue_copy(copy_geom(p, t.b, t.s_first, t.span, t.Li), stage_s, bar);
     }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __syncthreads();
@@ -113,17 +114,11 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) spec_kernel(const KParams 
         }
         float2 a[32];
         if (t.valid0) {
-            const float *row = p.wav + t.b * p.row_stride;
-            const int delta = stage_delta(row, t);
+            const CopyGeom g = copy_geom(p, t.b, t.s_first, t.span, t.Li);
+            const int delta = g.delta;
             mbar_wait(bar, parity);
             parity ^= 1;
-            if (t.s_first < 0 || t.s_first + t.span > t.Li) {
-                for (int i = lane; i < t.span; i += 32) {
-                    const int s = t.s_first + i;
-                    if (s < 0 || s >= t.Li) stage[i + delta] = __ldg(row + reflect_index(s, t.Li));
-                }
-                __syncwarp();
-            }
+            if (g.patch) patch_stage(p, t.b, t.s_first, t.span, t.Li, g, stage, lane);
             const float *x0 = stage + delta + lane;
             if (kPair) {
                 const float *x1 = x0 + (t.valid1 ? p.hop : 0);
@@ -151,13 +146,13 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) spec_kernel(const KParams 
         // prefetch this warp's next task (its task index is task + stride)
         if (lane == 0 && task + stride < p.n_tasks) {
             const Task n = decode_task<kPair>(p, cb, cq);
-            if (n.valid0) issue_stage<kPair>(p, n, stage, bar);
+            if (n.valid0) issue_copy(copy_geom(p, n.b, n.s_first, n.span, n.Li), stage_s, bar);
         }
         if (lane == 0) {
             SpecSlot s;
             s.n_frames = have ? (kPair && p.pair_frames == 2 ? (t.t0 + 1 < p.T ? 2 : 1) : 1) : 0;
             s.zero = have && !t.valid0;
-            s.row0 = have ? (t.b * p.n_freq) * (long long)p.T + t.t0 : 0;
+            s.row0 = have ? (t.b * p.n_freq_out) * (long long)p.T + t.t0 : 0;
             if (have && kPair && p.pair_frames == 2 && t.valid0 && !t.valid1 && t.t0 + 1 < p.T) s.zero = 2;  // second frame only
             s_slot[warp] = s;
         }
@@ -210,10 +205,11 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) spec_kernel(const KParams 
             if (f < s.n_frames) {
                 const bool zero = s.zero == 1 || (s.zero == 2 && f == 1);
                 const long long off = s.row0 + f;
-                for (int r = r0; r < p.n_freq; r += kRowsPerPass) {
+                for (int r = r0; r < p.n_freq_out; r += kRowsPerPass) {  // output row r = physical bin r * bin_step
                     const long long o = off + (long long)r * p.T;
-                    p.out_a[o] = zero ? 0.f : tile_a[r * kRowStride + col];
-                    if constexpr (kTwo) p.out_b[o] = zero ? 0.f : tile_b[r * kRowStride + col];
+                    const int ti = r * p.bin_step * kRowStride + col;
+                    p.out_a[o] = zero ? 0.f : tile_a[ti];
+                    if constexpr (kTwo) p.out_b[o] = zero ? 0.f : tile_b[ti];
                 }
             }
         }

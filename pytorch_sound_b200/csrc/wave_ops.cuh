@@ -2,6 +2,7 @@
 //   pre-emphasis        y[n] = x[n] - c x[n-1], y[0] = x[0] - c x[1]      models/sound.py:66-81 (PreEmphasis.forward)
 //   RMS volume norm     y = x / (std(x) / 10^(dB/10)), std over the tensor utils/calculate.py:56-63 (volume_norm_log_torch)
 //   mel -> MFCC         out[b, c, t] = sum_m dct[c, m] mel[b, m, t]       models/transforms.py:419-430 (MelToMFCC.forward)
+//   STFT-loss terms     per-clip sums of multi_stft_loss                  models/sound.py:139-141
 // All three are HBM-bound streaming kernels (8, 8 and 4 (M + C) / M bytes per element); grids are sized in
 // multiples of the SM count and every global access is a full 128-byte line per warp.
 #pragma once
@@ -67,6 +68,58 @@ __global__ void __launch_bounds__(256) scale_by_std_kernel(const float *__restri
     const float k = gain / (float)sqrt(var > 0.0 ? var : 0.0);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = x[i] * k;
+}
+
+// multi_stft_loss reductions (models/sound.py:139-141): for every clip b over its n = F * T magnitudes
+//   acc[3 b + 0] = sum (t - p)^2,  acc[3 b + 1] = sum t^2,  acc[3 b + 2] = sum |ln(t + eps) - ln(p + eps)|
+// One streaming pass over both magnitude tensors (8 bytes per element, HBM-bound); double accumulation, one
+// atomicAdd per quantity per CTA.  grid = (chunks, B).
+__global__ void __launch_bounds__(256) stft_loss_partial_kernel(const float *__restrict__ pm, const float *__restrict__ tm,
+                                                                 long long B, long long n, float eps, double *acc) {
+    for (long long b = blockIdx.y; b < B; b += gridDim.y) {
+        const float *pr = pm + b * n, *tr = tm + b * n;
+        double d2 = 0.0, t2 = 0.0, l1 = 0.0;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+            const float pv = pr[i], tv = tr[i];
+            const float d = tv - pv;
+            d2 += (double)(d * d);
+            t2 += (double)(tv * tv);
+            l1 += (double)fabsf(logf(tv + eps) - logf(pv + eps));
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+            t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+        }
+        __shared__ double sh[3][8];
+        const int w = threadIdx.x >> 5;
+        __syncthreads();  // previous clip's partials consumed
+        if ((threadIdx.x & 31) == 0) sh[0][w] = d2, sh[1][w] = t2, sh[2][w] = l1;
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            double v = 0.0;
+            for (int k = 0; k < (int)(blockDim.x >> 5); ++k) v += sh[threadIdx.x][k];
+            atomicAdd(acc + 3 * b + threadIdx.x, v);
+        }
+    }
+}
+// out[0] += mean_b sqrt(acc[3b] / acc[3b+1])      (spectral convergence, :139)
+// out[1] += mean_b acc[3b+2] / n                   (log-magnitude L1, :140)
+// Accumulates, so the resolutions of one multi_stft_loss call add up in the same two floats.
+__global__ void stft_loss_final_kernel(const double *acc, long long B, long long n, float *out) {
+    double sc = 0.0, mg = 0.0;
+    for (long long b = threadIdx.x; b < B; b += 32) {
+        sc += sqrt(acc[3 * b]) / sqrt(acc[3 * b + 1]);
+        mg += acc[3 * b + 2];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sc += __shfl_xor_sync(0xffffffffu, sc, o);
+        mg += __shfl_xor_sync(0xffffffffu, mg, o);
+    }
+    if (threadIdx.x == 0) {
+        out[0] += (float)(sc / (double)B);
+        out[1] += (float)(mg / (double)B / (double)n);
+    }
 }
 
 // mel (B, M, T) -> mfcc (B, C, T).  A warp owns 32 consecutive (b, t) columns (every global access a contiguous

@@ -29,9 +29,14 @@ def _check_wav(wav: torch.Tensor) -> torch.Tensor:
 
 
 def run(plan: "_lib.Plan", wav: torch.Tensor, epi: Optional["_lib.Epilogue"], want_mel: bool = True,
-        spec_kind: int = _lib.SPEC_NONE, lengths: Optional[torch.Tensor] = None
+        spec_kind: int = _lib.SPEC_NONE, lengths: Optional[torch.Tensor] = None,
+        out: Optional[torch.Tensor] = None, frame_mask: Optional[torch.Tensor] = None
         ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
-    """Launch the fused kernel on wav's device / current stream. Returns (mel, out_a, out_b)."""
+    """Launch the fused kernel on wav's device / current stream. Returns (mel, out_a, out_b).
+
+    `out`: optional preallocated contiguous (B, n_mels, T) float32 CUDA tensor for the mel frames (e.g. a slice of a
+    symmetric-memory gather buffer).  `frame_mask`: optional (B, T) float32 tensor the same launch fills with the
+    SpectrogramMasker frame mask."""
     wav = _check_wav(wav)
     dev = wav.device
     if dev.index != plan.device_index:
@@ -41,7 +46,15 @@ def run(plan: "_lib.Plan", wav: torch.Tensor, epi: Optional["_lib.Epilogue"], wa
     n_freq = plan.cfg.n_fft // 2 + 1
     mel = out_a = out_b = None
     if want_mel:
-        mel = torch.empty((B, plan.cfg.n_mels, T), device=dev, dtype=torch.float32)
+        if out is not None:
+            if out.shape != (B, plan.cfg.n_mels, T) or out.dtype != torch.float32 or out.device != dev or not out.is_contiguous():
+                raise ValueError(f"out must be a contiguous float32 {(B, plan.cfg.n_mels, T)} tensor on {dev}")
+            mel = out
+        else:
+            mel = torch.empty((B, plan.cfg.n_mels, T), device=dev, dtype=torch.float32)
+    if frame_mask is not None and (frame_mask.shape != (B, T) or frame_mask.dtype != torch.float32 or
+                                   frame_mask.device != dev or not frame_mask.is_contiguous()):
+        raise ValueError(f"frame_mask must be a contiguous float32 {(B, T)} tensor on {dev}")
     if spec_kind != _lib.SPEC_NONE:
         out_a = torch.empty((B, n_freq, T), device=dev, dtype=torch.float32)
         if spec_kind in (_lib.SPEC_MAG_PHASE, _lib.SPEC_RE_IM):
@@ -56,11 +69,12 @@ def run(plan: "_lib.Plan", wav: torch.Tensor, epi: Optional["_lib.Epilogue"], wa
         return mel, out_a, out_b
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = _lib.lib().b200mel_forward(
-            plan.handle, wav.data_ptr(), B, L, wav.stride(0) if B > 1 else max(L, 1), len_ptr,
-            C.byref(epi) if epi is not None else None, mel.data_ptr() if mel is not None else None, spec_kind,
-            out_a.data_ptr() if out_a is not None else None, out_b.data_ptr() if out_b is not None else None,
-            C.c_void_p(stream))
+        io = _lib.IO(C.sizeof(_lib.IO), spec_kind, wav.data_ptr(), B, L, wav.stride(0) if B > 1 else max(L, 1), len_ptr,
+                     mel.data_ptr() if mel is not None else None, out_a.data_ptr() if out_a is not None else None,
+                     out_b.data_ptr() if out_b is not None else None,
+                     frame_mask.data_ptr() if frame_mask is not None else None)
+        rc = _lib.lib().b200mel_forward_io(plan.handle, C.byref(io), C.byref(epi) if epi is not None else None,
+                                           C.c_void_p(stream))
     _lib.check(rc)
     return mel, out_a, out_b
 
@@ -125,3 +139,20 @@ def mel_to_mfcc(mel: torch.Tensor, dct: torch.Tensor) -> torch.Tensor:
                                             C.c_void_p(torch.cuda.current_stream(mel.device).cuda_stream))
     _lib.check(rc)
     return out
+
+
+def stft_loss_terms(pred_mag: torch.Tensor, target_mag: torch.Tensor, eps: float, out2: torch.Tensor) -> None:
+    """Adds one resolution's (spectral-convergence, log-magnitude) terms of multi_stft_loss (models/sound.py:139-141)
+    into the 2-float CUDA tensor `out2`."""
+    _check_cuda_f32(pred_mag, "pred magnitudes")
+    _check_cuda_f32(target_mag, "target magnitudes")
+    if pred_mag.shape != target_mag.shape or pred_mag.dim() != 3:
+        raise ValueError(f"expected two (B, F, T) tensors, got {tuple(pred_mag.shape)} and {tuple(target_mag.shape)}")
+    pred_mag, target_mag = pred_mag.contiguous(), target_mag.contiguous()
+    B, F, T = pred_mag.shape
+    scratch = torch.empty(3 * B, device=pred_mag.device, dtype=torch.float64)
+    with torch.cuda.device(pred_mag.device):
+        rc = _lib.lib().b200mel_stft_loss_terms(pred_mag.data_ptr(), target_mag.data_ptr(), B, F * T, float(eps),
+                                                scratch.data_ptr(), out2.data_ptr(),
+                                                C.c_void_p(torch.cuda.current_stream(pred_mag.device).cuda_stream))
+    _lib.check(rc)

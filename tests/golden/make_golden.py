@@ -221,9 +221,78 @@ def extras():
     print("wrote", path, {k: v.shape for k, v in out.items()})
 
 
+def round2():
+    """tests/golden/reference_round2.npz: the reference's multi_stft_loss (models/sound.py:106-147), its STFT /
+    LogMelSpectrogram at transform sizes below 1024, and SpectrogramMasker (models/transforms.py:397-416).
+
+    Two more shims, both for code that hard-codes `.cuda()` in the reference (models/sound.py:113-117,
+    models/transforms.py:405-406) and therefore cannot run on this GPU-less container as written:
+    `torch.nn.Module.cuda` is a no-op while this function runs.  The arithmetic is untouched."""
+    import torch
+
+    sys.path.insert(0, REF)
+    real_cuda = torch.nn.Module.cuda
+    torch.nn.Module.cuda = lambda self, device=None: self
+    try:
+        from pytorch_sound.models import transforms as T
+        from pytorch_sound.models import sound as S
+
+        from oracle import mel_oracle
+
+        torch.set_num_threads(1)
+        out = {}
+        target = mel_oracle.synth_clips(3, 16000, 22050, seed=20261017 + 7000)
+        rng = np.random.default_rng(11)
+        pred = (0.9 * target + 0.02 * rng.standard_normal(target.shape)).astype(np.float32)
+        out["loss.pred"], out["loss.target"] = pred, target
+        params = [(1024, 600, 120), (2048, 1200, 240), (512, 240, 50)]
+        out["loss.params"] = np.array(params, dtype=np.int64)
+        with torch.no_grad():
+            tot, sc, mag = S.multi_stft_loss(torch.from_numpy(pred), torch.from_numpy(target), params)
+            out["loss.values"] = np.array([float(tot), float(sc), float(mag)], dtype=np.float64)
+            tot2, sc2, mag2 = S.multi_stft_loss(torch.from_numpy(pred), torch.from_numpy(target), [(512, 512, 128)], eps=1e-3)
+            out["loss.values_512"] = np.array([float(tot2), float(sc2), float(mag2)], dtype=np.float64)
+            for fft, win, hop in params:
+                st = S.STFT(win, hop, win, fft)  # = STFTTorchAudio(filter_length=win, hop_length=hop, win_length=win, n_fft=fft)
+                out[f"loss.target_mag_{fft}"] = st.transform(torch.from_numpy(target[:1]))[0].numpy()
+
+            clips = mel_oracle.synth_clips(4, 6000, 22050, seed=20261017)
+            out["clips.wav"] = clips
+            xt = torch.from_numpy(clips)
+            for n, hop in ((512, 128), (256, 64), (128, 100)):
+                mag_, ph_ = T.STFT(filter_length=n, hop_length=hop).transform(xt)
+                out[f"clips.stft{n}_mag"], out[f"clips.stft{n}_phase"] = mag_.numpy(), ph_.numpy()
+            re, im = T.STFTTorchAudio(filter_length=400, hop_length=160, win_length=400, n_fft=512)(xt)
+            out["clips.stfta_win400_fft512_re"], out["clips.stfta_win400_fft512_im"] = re.numpy(), im.numpy()
+            x16 = mel_oracle.synth_clips(3, 8000, 16000, seed=20261017 + 5000)
+            out["c16.wav"] = x16
+            out["c16.logmel512"] = T.LogMelSpectrogram(16000, 40, 512, 512, 128, -50, 30, 0.0, 8000.0)(torch.from_numpy(x16)).numpy()
+            out["c16.audio2mel512"] = T.Audio2Mel(n_fft=512, hop_length=128, win_length=512, sampling_rate=16000,
+                                                  n_mel_channels=40)(torch.from_numpy(x16).unsqueeze(1)).numpy()
+
+            # SpectrogramMasker on pad_collate_fn-style masks (ones over the valid samples)
+            for win, hop, L, lens in ((1024, 256, 22050, [22050, 1, 700, 12345, 21800]), (800, 200, 6000, [6000, 4500, 5999, 399])):
+                mask = np.zeros((len(lens), L), dtype=np.float32)
+                for i, n in enumerate(lens):
+                    mask[i, :n] = 1
+                out[f"masker.{win}_{hop}.lengths"] = np.array(lens, dtype=np.int64)
+                out[f"masker.{win}_{hop}.L"] = np.array(L)
+                out[f"masker.{win}_{hop}.out"] = T.SpectrogramMasker(win, hop)(torch.from_numpy(mask)).numpy()
+    finally:
+        torch.nn.Module.cuda = real_cuda
+    path = os.path.join(HERE, "reference_round2.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    if "--extras-only" not in sys.argv:
-        main()
-    else:
+    if "--round2-only" in sys.argv:
         install_shims()
-    extras()
+        round2()
+    else:
+        if "--extras-only" not in sys.argv:
+            main()
+        else:
+            install_shims()
+        extras()
+        round2()

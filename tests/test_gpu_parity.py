@@ -352,7 +352,10 @@ def test_spectrogram_masker_on_cuda(torch_cuda):
         for i, n in enumerate(lens):
             mask[i, :n] = 1
         m = F.pad(F.pad(mask, [0, win // 2], value=0.), [win // 2, 0], value=1.)
-        ref = torch.ceil(F.conv1d(m.unsqueeze(1), torch.full((1, 1, win), 1.0 / win, device="cuda"), stride=hop).squeeze(1))
+        # the reference's mean filter in float64 (its fp32 sum of win x fl(1/win) can exceed 1 for windows that are not a
+        # power of two, which ceil() turns into 2 — a defect that is not matched, see tests/test_oracle_golden.py)
+        ref = torch.ceil(F.conv1d(m.double().unsqueeze(1), torch.full((1, 1, win), 1.0 / win, device="cuda", dtype=torch.float64),
+                                  stride=hop).squeeze(1) - 1e-9).float()
         masker = T.SpectrogramMasker(win, hop)
         got = masker(mask)
         assert got.is_cuda and got.shape == ref.shape and torch.equal(got, ref)

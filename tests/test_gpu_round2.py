@@ -1,0 +1,156 @@
+"""Round-2 GPU parity: transform sizes below 1024, multi_stft_loss, the fast-path / generic kernel pair, misaligned
+tensors (the bulk-copy clamp), the fused frame mask.  Golden values come from the reference itself
+(tests/golden/reference_round2.npz, made by tests/golden/make_golden.py --round2-only).  Needs a B200: `-m gpu`."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import mel_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+GEO = dict(sample_rate=22050, mel_size=80, n_fft=1024, win_length=1024, hop_length=256, mel_min=0.0, mel_max=8000.0)
+
+
+@pytest.fixture(scope="module")
+def golden2():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_round2.npz"))
+
+
+@pytest.fixture(scope="module")
+def torch_cuda(built_lib):
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need CUDA"
+    return torch
+
+
+def cuda(torch, x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def test_small_transform_sizes_vs_reference(torch_cuda, golden2):
+    """STFT(filter_length=512 / 256 / 128), STFTTorchAudio(win 400 in n_fft 512), LogMelSpectrogram / Audio2Mel at
+    n_fft 512 against the reference's outputs (the kernel runs them as every r-th bin of the 1024-point transform
+    of the zero-extended frame)."""
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+
+    x = cuda(torch, golden2["clips.wav"])
+    for n, hop in ((512, 128), (256, 64), (128, 100)):
+        st = T.STFT(filter_length=n, hop_length=hop).cuda()
+        mag, phase = st.transform(x)
+        ref = golden2[f"clips.stft{n}_mag"]
+        assert mag.shape == ref.shape
+        assert np.abs(mag.cpu().numpy() - ref).max() < 3e-6 * ref.max()
+        assert np.abs(st.magnitude(x).cpu().numpy() - ref).max() < 3e-6 * ref.max()
+        strong = ref > 1e-2 * ref.max()
+        d = np.angle(np.exp(1j * (phase.cpu().numpy().astype(np.float64) - golden2[f"clips.stft{n}_phase"])))
+        assert np.abs(d[strong]).max() < 1e-3
+    re, im = T.STFTTorchAudio(filter_length=400, hop_length=160, win_length=400, n_fft=512).cuda()(x)
+    scale = np.abs(golden2["clips.stfta_win400_fft512_re"]).max()
+    assert re.shape == golden2["clips.stfta_win400_fft512_re"].shape
+    assert np.abs(re.cpu().numpy() - golden2["clips.stfta_win400_fft512_re"]).max() < 3e-6 * scale
+    assert np.abs(im.cpu().numpy() - golden2["clips.stfta_win400_fft512_im"]).max() < 3e-6 * scale
+    x16 = cuda(torch, golden2["c16.wav"])
+    y = T.LogMelSpectrogram(16000, 40, 512, 512, 128, -50, 30, 0.0, 8000.0).cuda()(x16)
+    assert y.shape == golden2["c16.logmel512"].shape
+    assert mo.parity_error(y.cpu().numpy(), golden2["c16.logmel512"]) < TOL
+    a = T.Audio2Mel(n_fft=512, hop_length=128, win_length=512, sampling_rate=16000, n_mel_channels=40).cuda()(x16.unsqueeze(1))
+    assert mo.parity_error(a.cpu().numpy(), golden2["c16.audio2mel512"]) < TOL
+    # and against the float64 oracle at sizes the fixtures do not hold
+    xs = mo.synth_clips(3, 3000, 22050, seed=5)
+    for n, hop, win in ((64, 16, 64), (32, 8, 32), (512, 100, 300), (2048, 300, 1200)):
+        mag = T.STFT(filter_length=n, hop_length=hop, win_length=win).cuda().magnitude(cuda(torch, xs)).cpu().numpy()
+        rm, _ = mo.stft_transform(xs, n, hop, win)
+        assert mag.shape == rm.shape and np.abs(mag - rm).max() < 3e-6 * rm.max(), (n, hop, win)
+    with pytest.raises(ValueError):
+        T.STFT(filter_length=4096, hop_length=1024).cuda().magnitude(cuda(torch, xs))  # not built: loud, no fallback
+    with pytest.raises(ValueError):
+        T.STFT(filter_length=400, hop_length=100).cuda().magnitude(cuda(torch, xs))
+
+
+def test_multi_stft_loss_vs_reference(torch_cuda, golden2):
+    """models/sound.py:120-147: the three scalars the reference returned on seeded (pred, target), at 1e-4."""
+    torch = torch_cuda
+    from pytorch_sound_b200.models.sound import multi_stft_loss
+
+    pred, target = cuda(torch, golden2["loss.pred"]), cuda(torch, golden2["loss.target"])
+    params = [tuple(int(v) for v in row) for row in golden2["loss.params"]]
+    got = [float(v) for v in multi_stft_loss(pred, target, params)]
+    np.testing.assert_allclose(got, golden2["loss.values"], rtol=1e-4)
+    np.testing.assert_allclose(got, mo.multi_stft_loss(golden2["loss.pred"], golden2["loss.target"], params), rtol=1e-4)
+    got = [float(v) for v in multi_stft_loss(pred, target, [(512, 512, 128)], eps=1e-3)]
+    np.testing.assert_allclose(got, golden2["loss.values_512"], rtol=1e-4)
+    assert got[0] == pytest.approx(got[1] + got[2], rel=1e-6)
+    zero = [float(v) for v in multi_stft_loss(target, target, params)]
+    assert zero == [0.0, 0.0, 0.0]
+
+
+def test_fast_and_generic_kernels_agree(torch_cuda):
+    """b200mel_forward picks the compile-time-specialised kernel (logmel_fast.cuh) for the common geometry and the
+    generic body when `lengths` is given: same arithmetic in the same order, so interior frames are bit-identical;
+    the last odd frame of a clip differs only by the rounding of its pair partner (<= 1e-6)."""
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+
+    for geo, L in ((GEO, 22050), (dict(GEO, sample_rate=16000), 8000), (dict(GEO, mel_max=None), 5000)):
+        x = cuda(torch, mo.synth_clips(9, L, geo["sample_rate"], seed=31))
+        lm = T.LogMelSpectrogram(**geo).cuda()
+        full = torch.full((9,), L, device="cuda", dtype=torch.int32)
+        y_fast, y_gen = lm(x), lm(x, lengths=full)
+        Tn = y_fast.shape[2]
+        even = Tn - (Tn & 1)  # frames that are first or second member of a complete pair
+        assert torch.equal(y_fast[:, :, :even], y_gen[:, :, :even])
+        assert float((y_fast - y_gen).abs().max()) < 1e-5
+        assert mo.parity_error(y_fast.cpu().numpy(), mo.log_mel_spectrogram(x.cpu().numpy(), **geo, clamp=False)) < TOL
+
+
+def test_misaligned_and_tight_tensors(torch_cuda):
+    """The bulk copies are widened to 16-byte boundaries but clamped to the tensor (include/b200mel.h): a waveform
+    tensor whose first / last byte is not 16-byte aligned (a view at an odd float offset into a larger buffer, rows
+    of 22050 floats) gives bit-identical results to an aligned copy, for the mel and the spectrum kernels."""
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+
+    B, L = 5, 22050
+    x = cuda(torch, mo.synth_clips(B, L, 22050, seed=77))
+    lm = T.LogMelSpectrogram(**GEO).cuda()
+    st = T.STFT(filter_length=1024, hop_length=256).cuda()
+    y0, m0 = lm(x), st.magnitude(x)
+    full = torch.full((B,), L, device="cuda", dtype=torch.int32)
+    g0 = lm(x, lengths=full)
+    for off in (1, 2, 3, 5):
+        buf = torch.full((B * L + 8,), float("nan"), device="cuda")  # NaN guard floats around the view
+        v = buf[off:off + B * L].view(B, L)
+        v.copy_(x)
+        assert v.data_ptr() % 16 == (4 * off) % 16
+        assert torch.equal(lm(v), y0), off
+        assert torch.equal(lm(v, lengths=full), g0), off
+        assert torch.equal(st.magnitude(v), m0), off
+    # strided rows: every row start has its own alignment
+    wide = torch.zeros(B, L + 3, device="cuda")
+    wide[:, :L] = x
+    assert torch.equal(lm(wide[:, :L]), y0)
+
+
+def test_frame_mask_from_the_same_launch(torch_cuda, golden2):
+    """LogMelSpectrogram(..., frame_mask=True): the (B, T) SpectrogramMasker mask (models/transforms.py:397-416)
+    written by the mel launch itself, against the reference's own masker output."""
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+
+    lens = golden2["masker.1024_256.lengths"]
+    L = int(golden2["masker.1024_256.L"])
+    x = cuda(torch, mo.synth_clips(len(lens), L, 22050, seed=3))
+    lengths = torch.from_numpy(lens.astype(np.int32)).cuda()
+    for i, n in enumerate(lens):
+        x[i, int(n):] = 0
+    lm = T.LogMelSpectrogram(**GEO).cuda()
+    y, fmask = lm(x, lengths=lengths, frame_mask=True)
+    np.testing.assert_array_equal(fmask.cpu().numpy(), golden2["masker.1024_256.out"])
+    assert torch.equal(y, lm(x, lengths=lengths))
+    _, ones = lm(x, frame_mask=True)  # without lengths every frame is valid
+    assert bool((ones == 1).all())

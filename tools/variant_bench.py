@@ -57,14 +57,23 @@ def main():
     for i, flags in enumerate(sys.argv[1:] or [""]):
         lib = os.path.join(ROOT, "gpurun_out", f"libb200mel_var{i}.so")
         os.makedirs(os.path.dirname(lib), exist_ok=True)
-        cmd = [build.find_nvcc()] + build.NVCC_FLAGS + flags.split() + ["-o", lib, "b200mel.cu"]
+        # words of the form ENV:NAME=VALUE set an environment variable of the timed child instead of an nvcc flag
+        env = dict(os.environ)
+        words = []
+        for w in flags.split():
+            if w.startswith("ENV:"):
+                k, _, v = w[4:].partition("=")
+                env[k] = v
+            else:
+                words.append(w)
+        cmd = [build.find_nvcc()] + build.NVCC_FLAGS + words + ["-o", lib, "b200mel.cu"]
         r = subprocess.run(cmd, cwd=build.CSRC, capture_output=True, text=True)
         if r.returncode:
             print(f"[{flags}] BUILD FAILED\n{r.stderr[-2000:]}")
             continue
         out = os.path.join(ROOT, "gpurun_out", f"var{i}.pt")
         r = subprocess.run([sys.executable, "-c", CHILD % dict(root=ROOT, lib=lib, out=out, B=B, L=L, geo=geo)],
-                           capture_output=True, text=True)
+                           capture_output=True, text=True, env=env)
         if r.returncode:
             print(f"[{flags}] RUN FAILED\n{r.stderr[-2000:]}")
             continue
