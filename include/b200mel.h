@@ -166,10 +166,14 @@ int b200mel_forward_io(const b200mel_plan *plan, const b200mel_io *io, const b20
 
 /* Same, but wav_host / out_mel_host are HOST pointers (pinned memory gives
  * asynchronous copies): H2D copy -> kernel -> D2H copy on `stream` using
- * plan-owned device staging that grows on demand (so this entry point is NOT
- * re-entrant on one plan).  It returns after enqueuing; the caller synchronises
- * the stream.  This is the "host buffers in, host buffers out" call the
- * reference's CPU modules correspond to (wav on CPU in, mel on CPU out). */
+ * plan-owned device staging that grows on demand.  The staging is kept PER
+ * STREAM (up to 8 streams per plan), so calls on different streams overlap —
+ * the copy of one batch under the kernel and the read-back of another — and
+ * calls on one stream are ordered by the stream.  It returns after enqueuing;
+ * the caller synchronises the stream(s).  This is the "host buffers in, host
+ * buffers out" call the reference's CPU modules correspond to (wav on CPU in,
+ * mel on CPU out; DataLoader pin_memory data/dataset.py:180 + to_device
+ * utils/tensor.py:15 on the way in). */
 int b200mel_forward_host(b200mel_plan *plan, const float *wav_host, int64_t B, int64_t L, int64_t row_stride,
                          const b200mel_epilogue *epi, float *out_mel_host, void *stream);
 
@@ -197,6 +201,18 @@ int b200mel_preemphasis(const float *x, int64_t B, int64_t L, int64_t x_row_stri
 int b200mel_volume_norm(const float *x, int64_t n, float target_db, float *y, double *scratch, void *stream);
 int b200mel_mel_to_mfcc(const float *mel, const float *dct, int64_t B, int32_t n_mels, int32_t n_mfcc, int64_t T,
                         float *out, void *stream);
+
+/* Multi-GPU: all-gather of the ranks' mel blocks by pulling from peer memory over NVLink (the reference
+ * has no distributed code, trainer.py:269-272 only strips nn.DataParallel prefixes).  Every rank holds a buffer with
+ * the same layout — `world` blocks back to back, block r = elements [block_offsets[r], block_offsets[r+1]) — and has
+ * just written ITS block into ITS buffer (b200mel_forward with out_mel pointing at the block).  peer_bufs is a HOST
+ * array of `world` device pointers: rank r's buffer as mapped into this process (e.g. the buffer_ptrs of
+ * torch.distributed._symmetric_memory; entry `rank` is ignored).  One launch copies every peer's own block into
+ * local_buf with 16-byte peer loads.  The caller orders it after a cross-rank barrier on `stream` (all blocks
+ * written) and must not let a rank overwrite its block while peers may still be pulling it (two alternating
+ * buffers + the next step's barrier give that, see pytorch_sound_b200/distributed.py). */
+int b200mel_gather_pull(float *local_buf, const float *const *peer_bufs, int32_t world, int32_t rank,
+                        const int64_t *block_offsets /* [world + 1] */, void *stream);
 
 /* Number of kernel launches issued through this library since load (all plans;
  * used by bench.py's gpu_launches claim). */

@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -114,7 +115,7 @@ struct b200mel_plan {
     bool pair;        // phys_n_fft == 1024: two frames per complex FFT
     int pair_frames;  // frames per task (2 in pair mode unless hop > n_fft, else 1)
     // device tables
-    float *d_window = nullptr, *d_window_t = nullptr;
+    float *d_window = nullptr;
     float2 *d_tw = nullptr, *d_tw_post = nullptr;
     MelEntry *d_mel_entries = nullptr;
     float *d_mel_w = nullptr;
@@ -126,9 +127,18 @@ struct b200mel_plan {
     int n_warps = 0, smem_bytes = 0;
     // spectrum-output kernel (spec_kernel.cuh): tw | window | mbarriers | slots | 8 warp regions | tile A | tile B
     int sp_off_bar = 0, sp_off_slots = 0, sp_off_regions = 0, sp_off_tiles = 0, sp_smem_bytes = 0;
-    // staging for forward_host
-    float *d_stage_in = nullptr, *d_stage_out = nullptr;
-    size_t stage_in_bytes = 0, stage_out_bytes = 0;
+    // staging for forward_host: one (input, output) pair per CUDA stream that has called it, so calls on different
+    // streams overlap (copy of one batch under the kernel / read-back of another); calls on one stream are ordered
+    // by the stream itself.  Guarded by host_mu.
+    struct HostStage {
+        void *stream = nullptr;
+        float *d_in = nullptr, *d_out = nullptr;
+        size_t in_bytes = 0, out_bytes = 0;
+        bool used = false;
+    };
+    static constexpr int kHostStages = 8;
+    HostStage host_stage[kHostStages];
+    std::mutex host_mu;
 };
 
 constexpr int kMaxSmem = 232448;
@@ -151,7 +161,7 @@ static int layout_smem(b200mel_plan *pl) {
     if (region < kXposeBytes) region = kXposeBytes;
     pl->region_bytes = (region + 127) & ~127;
     pl->off_window = 32 * 32 * 8;
-    pl->off_entries = pl->off_window + std::max(n_fft * 4, 32 * 36 * 4);
+    pl->off_entries = pl->off_window + n_fft * 4;
     pl->off_melw = pl->off_entries + pl->mel_rounds * 32 * (int)sizeof(MelEntry);
     pl->off_bar = pl->off_melw + pl->mel_w_len * 4;
     pl->off_regions = (pl->off_bar + (kMaxWarps + 1) * 8 + 127) & ~127;  // per-warp mbarriers + the table mbarrier
@@ -505,13 +515,6 @@ int b200mel_plan_create(const b200mel_config *cfg, b200mel_plan **out) {
         if ((e = cudaMalloc(&pl->d_tw, tw.size() * sizeof(float2))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc"); break; }
         if ((e = cudaMalloc(&pl->d_tw_post, twp.size() * sizeof(float2))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc"); break; }
         cudaMemcpy(pl->d_window, win.data(), N * sizeof(float), cudaMemcpyHostToDevice);
-        if (N == 1024) {  // lane-major copy: row l = w[32 j + l], j = 0..31, rows 36 floats apart
-            std::vector<float> wt(32 * 36, 0.f);
-            for (int l = 0; l < 32; ++l)
-                for (int j = 0; j < 32; ++j) wt[l * 36 + j] = win[32 * j + l];
-            if ((e = cudaMalloc(&pl->d_window_t, wt.size() * sizeof(float))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc"); break; }
-            cudaMemcpy(pl->d_window_t, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice);
-        }
         cudaMemcpy(pl->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice);
         e = cudaMemcpy(pl->d_tw_post, twp.data(), twp.size() * sizeof(float2), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpy(tables)"); break; }
@@ -558,12 +561,13 @@ int b200mel_plan_set_filterbank(b200mel_plan *plan, const float *weights, int32_
 int b200mel_plan_destroy(b200mel_plan *pl) {
     if (!pl) return B200MEL_OK;
     cudaFree(pl->d_window);
-    cudaFree(pl->d_window_t);
     cudaFree(pl->d_tw);
     cudaFree(pl->d_tw_post);
     free_mel_tables(pl);
-    cudaFree(pl->d_stage_in);
-    cudaFree(pl->d_stage_out);
+    for (auto &hs : pl->host_stage) {
+        cudaFree(hs.d_in);
+        cudaFree(hs.d_out);
+    }
     delete pl;
     return B200MEL_OK;
 }
@@ -639,7 +643,6 @@ int b200mel_forward_io(const b200mel_plan *pl, const b200mel_io *io, const b200m
     p.pair_frames = pl->pair_frames;
     p.hann_full = (pl->pair && pl->cfg.win_length == pl->phys_n_fft && !g_table_window) ? 1 : 0;
     p.window = pl->d_window;
-    p.window_t = pl->d_window_t;
     p.tw = pl->d_tw;
     p.tw_post = pl->d_tw_post;
     p.mel_entries = pl->d_mel_entries;
@@ -741,32 +744,47 @@ int b200mel_forward_host(b200mel_plan *pl, const float *wav_host, int64_t B, int
     int64_t T = 0;
     frames_host(pl, L, &T);
     if (T <= 0) return fail(B200MEL_EINVAL, "forward_host: clip shorter than one frame");
-    const size_t in_bytes = (size_t)B * row_stride * sizeof(float);
+    const size_t in_bytes = ((size_t)(B - 1) * row_stride + L) * sizeof(float);
     const size_t out_bytes = (size_t)B * pl->cfg.n_mels * T * sizeof(float);
     cudaError_t e;
     cudaStream_t st = (cudaStream_t)stream;
-    if (in_bytes > pl->stage_in_bytes) {
-        cudaStreamSynchronize(st);
-        cudaFree(pl->d_stage_in);
-        pl->d_stage_in = nullptr;
-        pl->stage_in_bytes = 0;
-        if ((e = cudaMalloc(&pl->d_stage_in, in_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(stage_in)");
-        pl->stage_in_bytes = in_bytes;
+    b200mel_plan::HostStage *hs = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(pl->host_mu);
+        for (auto &c : pl->host_stage)
+            if (c.used && c.stream == stream) hs = &c;
+        if (!hs)
+            for (auto &c : pl->host_stage)
+                if (!c.used) {
+                    hs = &c;
+                    hs->used = true;
+                    hs->stream = stream;
+                    break;
+                }
+        if (!hs) return fail(B200MEL_EUNSUP, "forward_host: more than 8 distinct streams on one plan");
+        // growing a staging buffer frees the old one: wait for the work this stream still has on it (rare: first call /
+        // larger batch), never inside the steady state
+        if (in_bytes > hs->in_bytes) {
+            cudaStreamSynchronize(st);
+            cudaFree(hs->d_in);
+            hs->d_in = nullptr, hs->in_bytes = 0;
+            if ((e = cudaMalloc(&hs->d_in, in_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(stage_in)");
+            hs->in_bytes = in_bytes;
+        }
+        if (out_bytes > hs->out_bytes) {
+            cudaStreamSynchronize(st);
+            cudaFree(hs->d_out);
+            hs->d_out = nullptr, hs->out_bytes = 0;
+            if ((e = cudaMalloc(&hs->d_out, out_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(stage_out)");
+            hs->out_bytes = out_bytes;
+        }
     }
-    if (out_bytes > pl->stage_out_bytes) {
-        cudaStreamSynchronize(st);
-        cudaFree(pl->d_stage_out);
-        pl->d_stage_out = nullptr;
-        pl->stage_out_bytes = 0;
-        if ((e = cudaMalloc(&pl->d_stage_out, out_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(stage_out)");
-        pl->stage_out_bytes = out_bytes;
-    }
-    if ((e = cudaMemcpyAsync(pl->d_stage_in, wav_host, in_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+    if ((e = cudaMemcpyAsync(hs->d_in, wav_host, in_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess)
         return cuda_fail(e, "cudaMemcpyAsync(H2D)");
-    int rc = b200mel_forward(pl, pl->d_stage_in, B, L, row_stride, nullptr, epi, pl->d_stage_out, B200MEL_SPEC_NONE,
-                             nullptr, nullptr, stream);
+    int rc = b200mel_forward(pl, hs->d_in, B, L, row_stride, nullptr, epi, hs->d_out, B200MEL_SPEC_NONE, nullptr, nullptr,
+                             stream);
     if (rc) return rc;
-    if ((e = cudaMemcpyAsync(out_mel_host, pl->d_stage_out, out_bytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+    if ((e = cudaMemcpyAsync(out_mel_host, hs->d_out, out_bytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
         return cuda_fail(e, "cudaMemcpyAsync(D2H)");
     return B200MEL_OK;
 }
@@ -843,6 +861,30 @@ int b200mel_stft_loss_terms(const float *pred_mag, const float *target_mag, int6
     g_launches.fetch_add(2);
     e = cudaGetLastError();
     return e == cudaSuccess ? B200MEL_OK : cuda_fail(e, "stft_loss_terms launch");
+}
+
+int b200mel_gather_pull(float *local_buf, const float *const *peer_bufs, int32_t world, int32_t rank,
+                        const int64_t *block_offsets, void *stream) {
+    if (!local_buf || !peer_bufs || !block_offsets) return fail(B200MEL_EINVAL, "gather_pull: null pointer");
+    if (world < 1 || world > 16 || rank < 0 || rank >= world) return fail(B200MEL_EINVAL, "gather_pull: need 1 <= world <= 16, 0 <= rank < world");
+    PullArgs a;
+    memset(&a, 0, sizeof(a));
+    a.world = world, a.rank = rank;
+    for (int r = 0; r <= world; ++r) {
+        a.off[r] = block_offsets[r];
+        if (r && a.off[r] < a.off[r - 1]) return fail(B200MEL_EINVAL, "gather_pull: block offsets must be non-decreasing");
+    }
+    for (int r = 0; r < world; ++r) {
+        a.peer[r] = peer_bufs[r];
+        if (r != rank && !a.peer[r] && a.off[r + 1] > a.off[r]) return fail(B200MEL_EINVAL, "gather_pull: null peer buffer");
+    }
+    if (world == 1 || a.off[world] == a.off[0]) return B200MEL_OK;
+    int sms = 0;
+    if (int rc = current_sms(&sms)) return rc;
+    gather_pull_kernel<<<sms * 2, 512, 0, (cudaStream_t)stream>>>(local_buf, a);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? B200MEL_OK : cuda_fail(e, "gather_pull launch");
 }
 
 int b200mel_mel_to_mfcc(const float *mel, const float *dct, int64_t B, int32_t n_mels, int32_t n_mfcc, int64_t T,

@@ -94,7 +94,6 @@ struct KParams {
     int hann_full;    // 1: win_length == n_fft, the kernel may generate the periodic Hann instead of reading the table
     // global copies of the CTA tables
     const float *window;    // [n_fft], periodic Hann centre-padded, pre-scaled by 0.5
-    const float *window_t;  // [32][36] lane-major copy of the same table (experimental fast-path variant)
     const float2 *tw;       // [16][32][2]  tw[((j >> 1) * 32 + lane) * 2 + (j & 1)] = exp(-2 pi i j lane / 1024)
     const float2 *tw_post;  // [32]      exp(-2 pi i lane / 2048)            (split mode)
     const MelEntry *mel_entries;  // [rounds][32]
@@ -612,17 +611,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
                 load_windowed_pair(a, x0, s_win, hann_cs, p, lane, valid1);
             } else {
                 const float2 *w2 = reinterpret_cast<const float2 *>(s_win);
-#ifdef B200MEL_SPLIT_LDS64
-                // Experiment for the next round (VB_WORKLOAD=C4 tools/variant_bench.py "" "-DB200MEL_SPLIT_LDS64"): the
-                // even / odd sample pair of a lane is one aligned 64-bit load whenever the stage shift is even (always
-                // for 8-byte aligned rows of even length) — 32 conflict-free LDS.64 instead of 64 two-way conflicting
-                // LDS.32 per task.
+                // The even / odd sample pair of a lane is ONE aligned 64-bit load whenever the stage shift is even (always
+                // for 8-byte aligned rows of even length): 32 conflict-free LDS.64 instead of 64 two-way conflicting
+                // LDS.32 per task (measured at C4: 49.9 -> 48.5 us).
                 if ((d.delta & 1) == 0) {
                     const float2 *x2 = reinterpret_cast<const float2 *>(stage + d.delta) + lane;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) a[j] = __fmul2_rn(x2[32 * j], w2[32 * j + lane]);
                 } else
-#endif
 #pragma unroll
                 for (int j = 0; j < 32; ++j)  // samples 64 j + 2 lane, 64 j + 2 lane + 1
                     a[j] = __fmul2_rn(make_float2(x0[64 * j + lane], x0[64 * j + lane + 1]), w2[32 * j + lane]);

@@ -1,8 +1,24 @@
 """Clip-sharded multi-GPU extraction: one process per GPU, contiguous clip ranges per rank, no
 collective on the compute path; ONE all-gather of the rank's (B/G, M, T) mel block when every rank
 needs all frames.  The reference has no distributed code (only nn.DataParallel key
-stripping, trainer.py:269-272), so this is new surface, not a mirror."""
-from typing import Optional, Tuple
+stripping, trainer.py:269-272), so this is new surface, not a mirror.
+
+Two gathers:
+
+  mode="nccl"   `dist.all_gather_into_tensor` (NCCL over NVLink / NVSwitch); works on any backend (gloo in the CPU tests).
+  mode="fused"  the extraction kernel writes the rank's block straight into its slot of a SYMMETRIC buffer
+                (torch.distributed._symmetric_memory: the same allocation on every rank, peer-mapped), a device-side
+                barrier on the signal pads orders the ranks, and one pull kernel (b200mel_gather_pull: 16-byte loads
+                from the peers' buffers over NVLink) completes the local copy — no NCCL call, no host
+                synchronisation, no staging copy of the local block, and the result IS the symmetric buffer.
+                Three buffers rotate: a rank may only overwrite its block of a buffer once every peer has pulled
+                it, which its own NEXT barrier implies — so the extraction of step i is ordered after the gather of
+                step i-2 (automatic on one stream; with a separate communication stream wait on that gather's
+                event, as bench.py does) and still overlaps the gather of step i-1.
+                (`ShardedExtractor.__call__` returns a view that stays valid for the next two calls.)
+"""
+import ctypes as C
+from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -47,19 +63,99 @@ def all_gather_mel(local: torch.Tensor, n_clips: Optional[int] = None, group=Non
     return torch.cat([out[r * bmax:r * bmax + counts[r]] for r in range(world)], dim=0)
 
 
+class SymmetricGather:
+    """Peer-memory all-gather of clip-sharded (n_clips, M, T) float32 tensors (mode="fused").
+
+    `slot()` hands out this step's full-size symmetric buffer; the caller writes its own rows [a, b) into it
+    (the extraction kernel does, through `out=`), then `finish()` enqueues barrier + pull on the current stream and
+    returns the buffer, which now holds every rank's rows.  Buffers are (re)allocated when the shape grows — a
+    collective operation, so every rank must call with the same shapes in the same order."""
+
+    N_SLOTS = 3
+
+    def __init__(self, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self._symm = symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self._bufs: List[torch.Tensor] = []
+        self._hdls = []
+        self._capacity = 0
+        self._step = 0
+        self._shape = None
+
+    def _ensure(self, numel: int, device: torch.device) -> None:
+        if numel <= self._capacity:
+            return
+        self._bufs, self._hdls = [], []
+        for _ in range(self.N_SLOTS):
+            t = self._symm.empty(numel, dtype=torch.float32, device=device)
+            self._hdls.append(self._symm.rendezvous(t, self.group))
+            self._bufs.append(t)
+        self._capacity = numel
+
+    def slot(self, n_clips: int, n_mels: int, n_frames: int, device: torch.device) -> torch.Tensor:
+        numel = n_clips * n_mels * n_frames
+        self._ensure(numel, device)
+        self._shape = (n_clips, n_mels, n_frames)
+        return self._bufs[self._step % self.N_SLOTS][:numel].view(n_clips, n_mels, n_frames)
+
+    def finish(self) -> torch.Tensor:
+        from . import _lib
+
+        n_clips, n_mels, n_frames = self._shape
+        i = self._step % self.N_SLOTS
+        buf, hdl = self._bufs[i], self._hdls[i]
+        self._step += 1
+        per_clip = n_mels * n_frames
+        offs = [shard_range(n_clips, r, self.world)[0] * per_clip for r in range(self.world)] + [n_clips * per_clip]
+        # every rank has written its block (stream-ordered on each rank; the barrier is device-side on the signal pads)
+        hdl.barrier(channel=0)
+        peers = (C.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+        offs_c = (C.c_int64 * (self.world + 1))(*offs)
+        with torch.cuda.device(buf.device):
+            rc = _lib.lib().b200mel_gather_pull(buf.data_ptr(), peers, self.world, self.rank, offs_c,
+                                                C.c_void_p(torch.cuda.current_stream(buf.device).cuda_stream))
+        _lib.check(rc)
+        return buf[:n_clips * per_clip].view(n_clips, n_mels, n_frames)
+
+
 class ShardedExtractor:
     """Run `module` on this rank's contiguous shard of a clip batch that every rank holds (or can
-    index), optionally gathering the result.  `module(wav (b, L)) -> (b, M, T)`."""
+    index), optionally gathering the result.  `module(wav (b, L)) -> (b, M, T)`.
 
-    def __init__(self, module, group=None):
+    mode="nccl": module output, then all_gather_mel.  mode="fused": the module must accept `out=` (the extraction
+    modules of this package do); its kernel writes into the symmetric gather buffer and the gather is a device-side
+    barrier + one peer-pull kernel (SymmetricGather)."""
+
+    def __init__(self, module, group=None, mode: str = "nccl"):
+        if mode not in ("nccl", "fused"):
+            raise ValueError("mode must be 'nccl' or 'fused'")
         self.module = module
         self.group = group
+        self.mode = mode
+        self._sg: Optional[SymmetricGather] = None
 
     def __call__(self, wav_all: torch.Tensor, gather: bool = True) -> torch.Tensor:
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         a, b = shard_range(wav_all.shape[0], rank, world)
-        local = self.module(wav_all[a:b])
-        if gather and world > 1:
-            return all_gather_mel(local, wav_all.shape[0], self.group)
-        return local
+        if not (gather and world > 1):
+            return self.module(wav_all[a:b])
+        if self.mode == "nccl":
+            return all_gather_mel(self.module(wav_all[a:b]), wav_all.shape[0], self.group)
+        if self._sg is None:
+            self._sg = SymmetricGather(self.group)
+        n_mels, n_frames = self.out_shape(wav_all.shape[1])
+        full = self._sg.slot(wav_all.shape[0], n_mels, n_frames, wav_all.device)
+        if b > a:
+            self.module(wav_all[a:b], out=full[a:b])
+        return self._sg.finish()
+
+    def out_shape(self, n_samples: int) -> Tuple[int, int]:
+        """(n_mels, n_frames) of the module's output for clips of n_samples (fused mode needs it before the launch)."""
+        m = self.module
+        plan = m._plan(torch.device("cuda", torch.cuda.current_device()))
+        return plan.cfg.n_mels, plan.out_frames(n_samples)
