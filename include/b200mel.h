@@ -164,6 +164,17 @@ typedef struct b200mel_io {
 } b200mel_io;
 int b200mel_forward_io(const b200mel_plan *plan, const b200mel_io *io, const b200mel_epilogue *epi, void *stream);
 
+/* The mel filterbank as a tensor-core GEMM on magnitudes that already sit in device memory:
+ *   out_mel (B, n_mels, T) = epilogue( W (n_mels, n_fft/2+1) @ mag (B, n_fft/2+1, T) )
+ * Replaces `torch.matmul(self.mel_filter, magnitude)` + log + clamp of LogMelScale.forward
+ * (models/transforms.py:261-268; the same contraction as LogMelSpectrogram.forward :235-243 when the caller keeps the
+ * magnitudes, e.g. next to multi_stft_loss).  One launch of mel_tc_kernel: tcgen05.mma (UMMA 128 x n_mels x 16, bf16
+ * hi/lo split of both operands, three MMAs per K step) with the fp32 accumulator in TMEM, log epilogue on tcgen05.ld.
+ * `plan` supplies the filterbank (its bf16 limbs are built on first use, hence non-const); geometry limits: n_mels <=
+ * 128 and a filterbank that fits in shared memory (every BASELINE config with n_fft 1024), otherwise B200MEL_EUNSUP. */
+int b200mel_logmel_from_magnitude(b200mel_plan *plan, const float *mag, int64_t B, int64_t T,
+                                  const b200mel_epilogue *epi, float *out_mel, void *stream);
+
 /* Same, but wav_host / out_mel_host are HOST pointers (pinned memory gives
  * asynchronous copies): H2D copy -> kernel -> D2H copy on `stream` using
  * plan-owned device staging that grows on demand.  The staging is kept PER

@@ -56,6 +56,8 @@ SYMBOLS = {
     "b200mel_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                   C.POINTER(Epilogue), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200mel_forward_io": (C.c_int, [C.c_void_p, C.POINTER(IO), C.POINTER(Epilogue), C.c_void_p]),
+    "b200mel_logmel_from_magnitude": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Epilogue),
+                                                C.c_void_p, C.c_void_p]),
     "b200mel_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.POINTER(Epilogue),
                                        C.c_void_p, C.c_void_p]),
     "b200mel_launch_count": (C.c_int64, []),

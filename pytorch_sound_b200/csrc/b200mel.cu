@@ -26,6 +26,7 @@
 #include "fft32.cuh"
 #include "logmel_kernel.cuh"
 #include "logmel_fast.cuh"
+#include "mel_tc.cuh"
 #include "spec_kernel.cuh"
 #include "wave_ops.cuh"
 
@@ -122,6 +123,12 @@ struct b200mel_plan {
     int mel_rounds = 0, mel_w_len = 0;
     int top_groups = 16;  // 32-bin groups the pair kernel separates: 12 when the filterbank ends below bin 384
     int round_groups[kMaxMelRounds] = {0}, round_wbase[kMaxMelRounds] = {0};
+    // dense filterbank as uploaded (logical bins), kept for the tensor-core operator
+    std::vector<float> W_dense;
+    // tcgen05 mel GEMM (mel_tc.cuh): bf16 hi / lo limbs of the filterbank in the UMMA K-major core-matrix layout
+    uint16_t *d_tc_bhi = nullptr, *d_tc_blo = nullptr;
+    int tc_k_steps = 0, tc_n_pad = 0, tc_b_bytes = 0, tc_smem = 0;
+    std::mutex tc_mu;
     // shared-memory layout
     int off_window = 0, off_entries = 0, off_melw = 0, off_bar = 0, off_regions = 0, region_bytes = 0, stage_bytes = 0;
     int n_warps = 0, smem_bytes = 0;
@@ -311,6 +318,11 @@ static int build_mel_schedule(bool pair, const float *W, int n_mels, int F, MelS
 
 static int upload_filterbank(b200mel_plan *pl, const float *W_log, int n_mels, int F_log) {
     MelSchedule sch;
+    pl->W_dense.assign(W_log, W_log + (size_t)n_mels * F_log);
+    cudaFree(pl->d_tc_bhi);
+    cudaFree(pl->d_tc_blo);
+    pl->d_tc_bhi = pl->d_tc_blo = nullptr;  // rebuilt on demand from W_dense
+    pl->tc_k_steps = 0;
     // logical bin k lives at physical bin k * bin_step of the transform the kernel runs
     const int F = pl->phys_n_freq;
     std::vector<float> W_phys;
@@ -564,6 +576,8 @@ int b200mel_plan_destroy(b200mel_plan *pl) {
     cudaFree(pl->d_tw);
     cudaFree(pl->d_tw_post);
     free_mel_tables(pl);
+    cudaFree(pl->d_tc_bhi);
+    cudaFree(pl->d_tc_blo);
     for (auto &hs : pl->host_stage) {
         cudaFree(hs.d_in);
         cudaFree(hs.d_out);
@@ -861,6 +875,101 @@ int b200mel_stft_loss_terms(const float *pred_mag, const float *target_mag, int6
     g_launches.fetch_add(2);
     e = cudaGetLastError();
     return e == cudaSuccess ? B200MEL_OK : cuda_fail(e, "stft_loss_terms launch");
+}
+
+// fp32 -> bf16 (round to nearest even) on the host, as __float2bfloat16_rn does on the device
+static uint16_t bf16_rn(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static float bf16_to_float(uint16_t h) {
+    const uint32_t u = (uint32_t)h << 16;
+    float x;
+    memcpy(&x, &u, 4);
+    return x;
+}
+// Build (once per plan / filterbank) the bf16 hi / lo limbs of the filterbank in the layout mel_tc_kernel's B
+// descriptors address: [k_step][k / 8][n / 8][n % 8][k % 8].
+static int tc_prepare(b200mel_plan *pl) {
+    std::lock_guard<std::mutex> lock(pl->tc_mu);
+    if (pl->tc_k_steps) return B200MEL_OK;
+    const int n_mels = pl->cfg.n_mels, F = pl->n_freq;
+    if (n_mels <= 0 || pl->W_dense.empty()) return fail(B200MEL_EINVAL, "logmel_from_magnitude: plan has no filterbank");
+    int top = 0;
+    for (int m = 0; m < n_mels; ++m)
+        for (int k = 0; k < F; ++k)
+            if (pl->W_dense[(size_t)m * F + k] != 0.f) top = std::max(top, k + 1);
+    const int n_pad = (n_mels + 15) & ~15;
+    int k_steps = (std::max(top, 1) + 15) / 16;
+    k_steps += k_steps & 1;  // a pipeline stage is two K steps
+    const int b_bytes = k_steps * 2 * (n_pad / 8) * 128;
+    const int smem = 2 * b_bytes + 2 * kTcABuf + 2 * 8 + 16;
+    if (n_pad > kTcTmemCols || smem > kMaxSmem)
+        return fail(B200MEL_EUNSUP, "logmel_from_magnitude: filterbank too large for the shared-memory-resident tensor-core "
+                                    "kernel of this build (n_mels <= 128 and bins x mels x 4 bytes <= ~190 KB)");
+    std::vector<uint16_t> hi((size_t)b_bytes / 2, 0), lo((size_t)b_bytes / 2, 0);
+    for (int ks = 0; ks < k_steps; ++ks)
+        for (int kk = 0; kk < 16; ++kk)
+            for (int n = 0; n < n_pad; ++n) {
+                const int k = ks * 16 + kk;
+                const float w = (n < n_mels && k < F) ? pl->W_dense[(size_t)n * F + k] : 0.f;
+                const uint16_t h = bf16_rn(w);
+                const uint16_t l = bf16_rn(w - bf16_to_float(h));
+                const size_t off = ((size_t)ks * 2 * (n_pad / 8) * 128 + (size_t)(kk / 8) * (n_pad / 8) * 128 + (size_t)(n / 8) * 128 +
+                                    (size_t)(n % 8) * 16 + (size_t)(kk % 8) * 2) / 2;
+                hi[off] = h, lo[off] = l;
+            }
+    cudaError_t e;
+    if ((e = cudaMalloc(&pl->d_tc_bhi, b_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&pl->d_tc_blo, b_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    cudaMemcpy(pl->d_tc_bhi, hi.data(), b_bytes, cudaMemcpyHostToDevice);
+    if ((e = cudaMemcpy(pl->d_tc_blo, lo.data(), b_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+    if ((e = cudaFuncSetAttribute(mel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
+        return cuda_fail(e, "cudaFuncSetAttribute(mel_tc_kernel)");
+    pl->tc_n_pad = n_pad, pl->tc_b_bytes = b_bytes, pl->tc_smem = smem;
+    pl->tc_k_steps = k_steps;
+    return B200MEL_OK;
+}
+
+int b200mel_logmel_from_magnitude(b200mel_plan *pl, const float *mag, int64_t B, int64_t T, const b200mel_epilogue *epi,
+                                  float *out_mel, void *stream) {
+    if (!pl) return fail(B200MEL_EINVAL, "logmel_from_magnitude: null plan");
+    if (B < 0 || T < 0) return fail(B200MEL_EINVAL, "logmel_from_magnitude: negative shape");
+    if (B == 0 || T == 0) return B200MEL_OK;
+    if (!mag || !out_mel || !epi) return fail(B200MEL_EINVAL, "logmel_from_magnitude: null pointer");
+    if (epi->struct_size != (int32_t)sizeof(b200mel_epilogue)) return fail(B200MEL_EINVAL, "logmel_from_magnitude: epilogue struct_size mismatch");
+    if (epi->log_kind < 0 || epi->log_kind > 3) return fail(B200MEL_EINVAL, "logmel_from_magnitude: bad log_kind");
+    if (epi->norm_mel && !(epi->has_clamp_lo && epi->has_clamp_hi && epi->clamp_hi > epi->clamp_lo))
+        return fail(B200MEL_EINVAL, "logmel_from_magnitude: norm_mel needs clamp_lo < clamp_hi");
+    if (T > 0x7fffffff || B * T / kTcTileM > 0x7fffffff) return fail(B200MEL_EINVAL, "logmel_from_magnitude: too many frames");
+    if (int rc = tc_prepare(pl)) return rc;
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.mag = mag, p.out = out_mel;
+    p.n_cols = B * T;
+    p.T = (int)T, p.F = pl->n_freq, p.n_mels = pl->cfg.n_mels;
+    p.n_pad = pl->tc_n_pad, p.k_steps = pl->tc_k_steps;
+    p.b_hi = pl->d_tc_bhi, p.b_lo = pl->d_tc_blo, p.b_bytes = pl->tc_b_bytes;
+    p.lo = -INFINITY, p.hi = INFINITY, p.norm_scale = 1.f, p.norm_bias = 0.f, p.ep_floor = -INFINITY;
+    p.use_log = epi->log_kind != B200MEL_LOG_NONE;
+    if (epi->log_kind == B200MEL_LOG_LN_OFFSET) p.ep_offset = epi->log_arg;
+    else if (p.use_log) p.ep_floor = epi->log_arg;
+    p.log_scale = epi->log_kind == B200MEL_LOG_LOG10_FLOOR ? 0.301029995663981195f : 0.693147180559945309f;
+    if (epi->has_clamp_lo) p.lo = epi->clamp_lo;
+    if (epi->has_clamp_hi) p.hi = epi->clamp_hi;
+    if (epi->norm_mel) {
+        p.norm_scale = 2.0f / (p.hi - p.lo);
+        p.norm_bias = -p.lo * p.norm_scale - 1.0f;
+    }
+    long long tiles = (p.n_cols + kTcTileM - 1) / kTcTileM;
+    const int grid = (int)std::min<long long>(tiles, pl->num_sms);
+    mel_tc_kernel<<<grid, kTcThreads, pl->tc_smem, (cudaStream_t)stream>>>(p);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? B200MEL_OK : cuda_fail(e, "logmel_from_magnitude launch");
 }
 
 int b200mel_gather_pull(float *local_buf, const float *const *peer_bufs, int32_t world, int32_t rank,

@@ -156,3 +156,22 @@ def stft_loss_terms(pred_mag: torch.Tensor, target_mag: torch.Tensor, eps: float
                                                 scratch.data_ptr(), out2.data_ptr(),
                                                 C.c_void_p(torch.cuda.current_stream(pred_mag.device).cuda_stream))
     _lib.check(rc)
+
+
+def logmel_from_magnitude(plan: "_lib.Plan", mag: torch.Tensor, epi: "_lib.Epilogue") -> torch.Tensor:
+    """(B, n_fft//2+1, T) magnitudes -> (B, n_mels, T) through the tcgen05 / TMEM mel GEMM (b200mel_logmel_from_magnitude)."""
+    _check_cuda_f32(mag, "magnitude")
+    if mag.dim() != 3 or mag.shape[1] != plan.cfg.n_fft // 2 + 1:
+        raise ValueError(f"expected magnitudes (B, {plan.cfg.n_fft // 2 + 1}, T), got {tuple(mag.shape)}")
+    if mag.device.index != plan.device_index:
+        raise RuntimeError(f"plan lives on cuda:{plan.device_index}, magnitudes on {mag.device}")
+    mag = mag.contiguous()
+    B, _, T = mag.shape
+    out = torch.empty((B, plan.cfg.n_mels, T), device=mag.device, dtype=torch.float32)
+    if B == 0 or T == 0:
+        return out
+    with torch.cuda.device(mag.device):
+        rc = _lib.lib().b200mel_logmel_from_magnitude(plan.handle, mag.data_ptr(), B, T, C.byref(epi), out.data_ptr(),
+                                                      C.c_void_p(torch.cuda.current_stream(mag.device).cuda_stream))
+    _lib.check(rc)
+    return out

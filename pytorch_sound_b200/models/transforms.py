@@ -171,6 +171,34 @@ class LogMelSpectrogram(_PlanUser):
         return (mel, fm) if frame_mask else mel
 
 
+class LogMelScale(_PlanUser):
+    """pytorch_sound.models.transforms.LogMelScale (transforms.py:247-268): mel filterbank + log + clamp applied to a
+    MAGNITUDE spectrogram (B, n_fft//2+1, T) -> (B, mel_size, T).
+
+    The reference class cannot be constructed (`torch.Tensor(mel_filter, dtype=torch.float)` raises TypeError,
+    :258-259); its intended forward — `torch.matmul(self.mel_filter, magnitude)`,
+    `log(mel + log_offset)`, `clamp(min_db, max_db)` — is what runs here, as ONE tcgen05 tensor-core GEMM with the
+    accumulator in TMEM (csrc/mel_tc.cuh): the path's dense contraction, for callers that keep magnitudes around."""
+
+    _fb_buffer_name = 'mel_filter'
+
+    def __init__(self, sample_rate: int, mel_size: int, n_fft: int, min_db: float, max_db: float,
+                 mel_min: float = 0., mel_max: float = None):
+        super().__init__()
+        self.mel_size = mel_size
+        self.min_db = float(np.log(np.power(10, min_db / 10)))  # unconditional, unlike LogMelSpectrogram (:253-254)
+        self.max_db = float(np.log(np.power(10, max_db / 10)))
+        mel_filter = _lib.mel_filterbank(sample_rate, n_fft, mel_size, mel_min, mel_max)
+        self.register_buffer('mel_filter', torch.from_numpy(mel_filter))
+        self._fb_default = torch.from_numpy(mel_filter).clone()
+        self._plan_kwargs = dict(sample_rate=sample_rate, n_fft=n_fft, win_length=n_fft, hop_length=n_fft // 4,
+                                 n_mels=mel_size, fmin=mel_min, fmax=mel_max, pad_mode=_lib.PAD_CENTER)
+
+    def forward(self, magnitude: torch.Tensor, log_offset: float = 1e-6) -> torch.Tensor:
+        epi = _lib.make_epilogue(_lib.LOG_LN_OFFSET, log_offset, self.min_db, self.max_db)
+        return functional.logmel_from_magnitude(self._plan(magnitude.device), magnitude, epi)
+
+
 class STFTTorchAudio(_PlanUser):
     """Drop-in for pytorch_sound.models.transforms.STFTTorchAudio (transforms.py:271-319), analysis direction."""
 

@@ -91,9 +91,11 @@ def test_multi_stft_loss_vs_reference(torch_cuda, golden2):
 
 def test_fast_and_generic_kernels_agree(torch_cuda):
     """b200mel_forward picks the compile-time-specialised kernel (logmel_fast.cuh) for the common geometry and the
-    generic body when `lengths` is given: separately compiled instances of the same arithmetic, which agree to a few
-    ulp of the log-mel value (measured 2.4e-6; the bar is 1e-5, a tenth of the parity tolerance) — and each is
-    within 1e-4 of the float64 oracle on its own."""
+    generic body when `lengths` is given: separately compiled instances of the same arithmetic.  Complete frame pairs
+    agree to a few ulp of the log-mel value (measured 2.4e-6); the odd last frame of a clip is paired with the
+    reflected continuation of the clip in the fast kernel and with zeros in the generic one, so the fp32 rounding of
+    its pair partner differs (measured 1.4e-5 on noise-floor bands).  Bar: 3e-5, a third of the parity tolerance —
+    and each kernel is within 1e-4 of the float64 oracle on its own."""
     torch = torch_cuda
     from pytorch_sound_b200.models import transforms as T
 
@@ -102,7 +104,7 @@ def test_fast_and_generic_kernels_agree(torch_cuda):
         lm = T.LogMelSpectrogram(**geo).cuda()
         full = torch.full((9,), L, device="cuda", dtype=torch.int32)
         y_fast, y_gen = lm(x), lm(x, lengths=full)
-        assert float((y_fast - y_gen).abs().max()) < 1e-5
+        assert float((y_fast - y_gen).abs().max()) < 3e-5
         ref = mo.log_mel_spectrogram(x.cpu().numpy(), **geo, clamp=False)
         assert mo.parity_error(y_fast.cpu().numpy(), ref) < TOL and mo.parity_error(y_gen.cpu().numpy(), ref) < TOL
 
@@ -153,3 +155,36 @@ def test_frame_mask_from_the_same_launch(torch_cuda, golden2):
     assert torch.equal(y, lm(x, lengths=lengths))
     _, ones = lm(x, frame_mask=True)  # without lengths every frame is valid
     assert bool((ones == 1).all())
+
+
+def test_logmelscale_tcgen05_vs_oracle(torch_cuda):
+    """LogMelScale (models/transforms.py:247-268; the reference class itself raises TypeError at construction): the mel
+    filterbank as a tcgen05 tensor-core GEMM (bf16 hi/lo split, fp32 accumulator in TMEM) on magnitudes in HBM, against
+    the float64 product of the same filterbank and the same fp32 magnitudes — so only the GEMM's own error is seen."""
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+
+    for sr, n_mels, fmax, B, L in ((22050, 80, 8000.0, 7, 22050), (16000, 80, 8000.0, 33, 8000), (22050, 40, None, 3, 3000),
+                                   (22050, 128, 8000.0, 2, 5000)):
+        x = mo.synth_clips(B, L, sr, seed=11 + B)
+        x[0] *= 1e-4  # a quiet clip: bands far below the log offset
+        mag = T.STFT(filter_length=1024, hop_length=256).cuda().magnitude(cuda(torch, x))
+        lms = T.LogMelScale(sr, n_mels, 1024, -50, 30, 0.0, fmax).cuda()
+        y = lms(mag)
+        assert y.shape == (B, n_mels, mag.shape[2]) and y.dtype == torch.float32
+        fb = mo.mel_filterbank(sr, 1024, n_mels, 0.0, fmax).astype(np.float64)
+        ref = np.log(np.einsum("mf,bft->bmt", fb, mag.cpu().numpy().astype(np.float64)) + 1e-6)
+        ref = np.clip(ref, mo.db2log(-50), mo.db2log(30))
+        err = mo.parity_error(y.cpu().numpy(), ref)
+        print(f"LogMelScale tcgen05 sr={sr} mels={n_mels}: max err {err:.2e}")
+        assert err < TOL
+        # and it agrees with the fused kernel's own filterbank path on the same waveform
+        lm = T.LogMelSpectrogram(sr, n_mels, 1024, 1024, 256, -50, 30, 0.0, fmax).cuda()
+        assert float((lm(cuda(torch, x)) - y).abs().max()) < 2e-4
+    # tile boundaries: B * T not a multiple of 128, one clip, one frame
+    for B, Tn in ((1, 1), (1, 129), (5, 127), (3, 300)):
+        mag = torch.rand(B, 513, Tn, device="cuda") * 3
+        y = T.LogMelScale(22050, 80, 1024, -50, 30, 0.0, 8000.0).cuda()(mag)
+        fb = mo.mel_filterbank(22050, 1024, 80, 0.0, 8000.0).astype(np.float64)
+        ref = np.clip(np.log(np.einsum("mf,bft->bmt", fb, mag.cpu().numpy().astype(np.float64)) + 1e-6), mo.db2log(-50), mo.db2log(30))
+        assert mo.parity_error(y.cpu().numpy(), ref) < TOL, (B, Tn)

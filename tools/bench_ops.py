@@ -19,6 +19,10 @@ ops = {
     "STFT.transform (mag, phase)": (T.STFT(1024, 256).cuda(), lambda m, x: m.transform(x)),
     "STFTTorchAudio.forward (re, im)": (T.STFTTorchAudio(1024, 256).cuda(), lambda m, x: m(x)),
 }
+_mag = T.STFT(1024, 256).cuda()
+_mags = [_mag.magnitude(x) for x in xs]
+ops["LogMelScale.forward (tcgen05 mel GEMM on magnitudes in HBM)"] = (
+    T.LogMelScale(22050, 80, 1024, -50, 30, 0.0, 8000.0).cuda(), lambda m, x: m(_mags[[id(t) for t in xs].index(id(x))]))
 for name, (mod, fn) in ops.items():
     for x in xs:
         fn(mod, x)
