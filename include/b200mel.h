@@ -219,11 +219,24 @@ int b200mel_mel_to_mfcc(const float *mel, const float *dct, int64_t B, int32_t n
  * just written ITS block into ITS buffer (b200mel_forward with out_mel pointing at the block).  peer_bufs is a HOST
  * array of `world` device pointers: rank r's buffer as mapped into this process (e.g. the buffer_ptrs of
  * torch.distributed._symmetric_memory; entry `rank` is ignored).  One launch copies every peer's own block into
- * local_buf with 16-byte peer loads.  The caller orders it after a cross-rank barrier on `stream` (all blocks
- * written) and must not let a rank overwrite its block while peers may still be pulling it (two alternating
- * buffers + the next step's barrier give that, see pytorch_sound_b200/distributed.py). */
-int b200mel_gather_pull(float *local_buf, const float *const *peer_bufs, int32_t world, int32_t rank,
-                        const int64_t *block_offsets /* [world + 1] */, void *stream);
+ * local_buf with 16-byte peer loads.
+ * Ordering across ranks: peer_sync (nullable) is a HOST array of `world` device pointers to each rank's sync words
+ * (int32[world + 2], zero-initialised once, symmetric like the buffers): with it the kernel itself runs the barrier —
+ * it publishes "my block of this step is written" to every peer (system-scope release stores) and waits for all
+ * peers' flags of the same step (bounded spin, then a trap) before pulling; the step number lives in device memory,
+ * so the launch can be captured in a CUDA graph and replayed.  Every rank must launch once per step.  Without
+ * peer_sync the caller orders the launch after its own cross-rank barrier on `stream`.  Either way a rank must not
+ * overwrite its block while peers may still be pulling it: rotate three buffers and order the extraction of step i
+ * after this rank's gather of step i-2 (pytorch_sound_b200/distributed.py). */
+int b200mel_gather_pull(float *local_buf, const float *const *peer_bufs, int32_t *const *peer_sync, int32_t world,
+                        int32_t rank, const int64_t *block_offsets /* [world + 1] */, void *stream);
+/* Same gather with the COPY ENGINES doing the transfers: a one-CTA barrier kernel (peer_sync is required), then one
+ * device-to-device copy per peer on internal streams forked from and joined back into `stream`.  The extraction
+ * kernel is persistent and fills every SM, so an SM-resident pull cannot run beside it; the copy engines can — use
+ * this variant when the gather of step i is overlapped with the extraction of step i+1 on another stream, and
+ * b200mel_gather_pull (higher peak bandwidth, 16-byte peer loads) when the gather runs alone. */
+int b200mel_gather_copy(float *local_buf, const float *const *peer_bufs, int32_t *const *peer_sync, int32_t world,
+                        int32_t rank, const int64_t *block_offsets /* [world + 1] */, void *stream);
 
 /* Number of kernel launches issued through this library since load (all plans;
  * used by bench.py's gpu_launches claim). */

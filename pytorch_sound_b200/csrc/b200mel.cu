@@ -972,8 +972,30 @@ int b200mel_logmel_from_magnitude(b200mel_plan *pl, const float *mag, int64_t B,
     return e == cudaSuccess ? B200MEL_OK : cuda_fail(e, "logmel_from_magnitude launch");
 }
 
-int b200mel_gather_pull(float *local_buf, const float *const *peer_bufs, int32_t world, int32_t rank,
-                        const int64_t *block_offsets, void *stream) {
+// Internal streams / events of b200mel_gather_copy, one set per device, created on first use.
+struct GatherCtx {
+    bool ready = false;
+    cudaStream_t streams[15];
+    cudaEvent_t fork, join[15];
+};
+static GatherCtx g_gather[64];
+static std::mutex g_gather_mu;
+
+static int gather_impl(float *local_buf, const float *const *peer_bufs, int32_t *const *peer_sync, int32_t world,
+                       int32_t rank, const int64_t *block_offsets, void *stream, bool use_copy_engines);
+
+int b200mel_gather_pull(float *local_buf, const float *const *peer_bufs, int32_t *const *peer_sync, int32_t world,
+                        int32_t rank, const int64_t *block_offsets, void *stream) {
+    return gather_impl(local_buf, peer_bufs, peer_sync, world, rank, block_offsets, stream, false);
+}
+int b200mel_gather_copy(float *local_buf, const float *const *peer_bufs, int32_t *const *peer_sync, int32_t world,
+                        int32_t rank, const int64_t *block_offsets, void *stream) {
+    if (!peer_sync) return fail(B200MEL_EINVAL, "gather_copy: peer_sync is required (the barrier kernel orders the copies)");
+    return gather_impl(local_buf, peer_bufs, peer_sync, world, rank, block_offsets, stream, true);
+}
+
+static int gather_impl(float *local_buf, const float *const *peer_bufs, int32_t *const *peer_sync, int32_t world,
+                       int32_t rank, const int64_t *block_offsets, void *stream, bool use_copy_engines) {
     if (!local_buf || !peer_bufs || !block_offsets) return fail(B200MEL_EINVAL, "gather_pull: null pointer");
     if (world < 1 || world > 16 || rank < 0 || rank >= world) return fail(B200MEL_EINVAL, "gather_pull: need 1 <= world <= 16, 0 <= rank < world");
     PullArgs a;
@@ -986,14 +1008,49 @@ int b200mel_gather_pull(float *local_buf, const float *const *peer_bufs, int32_t
     for (int r = 0; r < world; ++r) {
         a.peer[r] = peer_bufs[r];
         if (r != rank && !a.peer[r] && a.off[r + 1] > a.off[r]) return fail(B200MEL_EINVAL, "gather_pull: null peer buffer");
+        a.peer_sync[r] = peer_sync ? reinterpret_cast<int *>(peer_sync[r]) : nullptr;
+        if (peer_sync && !a.peer_sync[r]) return fail(B200MEL_EINVAL, "gather_pull: null sync pointer");
     }
-    if (world == 1 || a.off[world] == a.off[0]) return B200MEL_OK;
+    if (world == 1) return B200MEL_OK;  // (an empty gather still runs the barrier: every rank must launch every step)
     int sms = 0;
     if (int rc = current_sms(&sms)) return rc;
-    gather_pull_kernel<<<sms * 2, 512, 0, (cudaStream_t)stream>>>(local_buf, a);
+    cudaStream_t st = (cudaStream_t)stream;
+    a.pull = use_copy_engines ? 0 : 1;
+    gather_pull_kernel<<<use_copy_engines ? 1 : sms * 2, 512, 0, st>>>(local_buf, a);
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? B200MEL_OK : cuda_fail(e, "gather_pull launch");
+    if (e != cudaSuccess) return cuda_fail(e, "gather launch");
+    if (!use_copy_engines) return B200MEL_OK;
+    // one device-to-device copy per peer, each on its own internal stream forked from (and joined back into) `stream`:
+    // the copy engines move the blocks while the SMs stay with the next extraction kernel
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if (dev < 0 || dev >= 64) return fail(B200MEL_EUNSUP, "gather_copy: device index out of range");
+    GatherCtx &gc = g_gather[dev];
+    {
+        std::lock_guard<std::mutex> lock(g_gather_mu);
+        if (!gc.ready) {
+            for (int i = 0; i < 15 && e == cudaSuccess; ++i) {
+                e = cudaStreamCreateWithFlags(&gc.streams[i], cudaStreamNonBlocking);
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&gc.join[i], cudaEventDisableTiming);
+            }
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&gc.fork, cudaEventDisableTiming);
+            if (e != cudaSuccess) return cuda_fail(e, "gather_copy: creating streams / events");
+            gc.ready = true;
+        }
+    }
+    if ((e = cudaEventRecord(gc.fork, st)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
+    for (int i = 1; i < world && e == cudaSuccess; ++i) {
+        const int r = (rank + i) % world;
+        const size_t bytes = (size_t)(a.off[r + 1] - a.off[r]) * sizeof(float);
+        if (!bytes) continue;
+        cudaStream_t cs = gc.streams[i - 1];
+        e = cudaStreamWaitEvent(cs, gc.fork, 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(local_buf + a.off[r], a.peer[r] + a.off[r], bytes, cudaMemcpyDeviceToDevice, cs);
+        if (e == cudaSuccess) e = cudaEventRecord(gc.join[i - 1], cs);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, gc.join[i - 1], 0);
+    }
+    return e == cudaSuccess ? B200MEL_OK : cuda_fail(e, "gather_copy: peer copies");
 }
 
 int b200mel_mel_to_mfcc(const float *mel, const float *dct, int64_t B, int32_t n_mels, int32_t n_mfcc, int64_t T,
@@ -1006,6 +1063,21 @@ int b200mel_mel_to_mfcc(const float *mel, const float *dct, int64_t B, int32_t n
         return fail(B200MEL_EUNSUP, "mel_to_mfcc: supports n_mels <= 128 and a DCT matrix of at most 48 KB");
     int sms = 0;
     if (int rc = current_sms(&sms)) return rc;
+    // Common shapes (the reference's MFCC_SIZE x MEL_SIZE = 40 x 80, settings.py:15-16, and any n_mfcc <= 64 over 40 / 80 /
+    // 128 mels): DCT matrix staged in constant memory by a stream-ordered device-to-device copy, weights as
+    // constant-bank operands.  (Calls on DIFFERENT streams with DIFFERENT matrices must not overlap: one staging buffer.)
+    if (!getenv("B200MEL_DCT_SMEM") && n_mfcc <= kDctConstRows && (n_mels == 40 || n_mels == 80 || n_mels == 128)) {
+        cudaError_t ce = cudaMemcpyToSymbolAsync(c_dct, dct, (size_t)n_mfcc * n_mels * sizeof(float), 0,
+                                                 cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+        if (ce != cudaSuccess) return cuda_fail(ce, "mel_to_mfcc: staging the DCT matrix");
+        const int g = grid_for(B * T, 128, sms);
+        if (n_mels == 40) dct_const_kernel<40><<<g, 128, 0, (cudaStream_t)stream>>>(mel, out, B, n_mfcc, (int)T);
+        else if (n_mels == 80) dct_const_kernel<80><<<g, 128, 0, (cudaStream_t)stream>>>(mel, out, B, n_mfcc, (int)T);
+        else dct_const_kernel<128><<<g, 128, 0, (cudaStream_t)stream>>>(mel, out, B, n_mfcc, (int)T);
+        g_launches.fetch_add(1);
+        cudaError_t le = cudaGetLastError();
+        return le == cudaSuccess ? B200MEL_OK : cuda_fail(le, "mel_to_mfcc launch");
+    }
     const int grid = grid_for(B * T * ((n_mfcc + kDctRows - 1) / kDctRows), 128, sms);  // a thread = one column x 8 rows
     if (n_mels <= 80)
         dct_kernel<80><<<grid, 128, sm, (cudaStream_t)stream>>>(mel, dct, out, B, n_mels, n_mfcc, (int)T);

@@ -127,28 +127,50 @@ __global__ void __launch_bounds__(kTcThreads, 1) mel_tc_kernel(const TcParams p)
     const long long n_tiles = (p.n_cols + kTcTileM - 1) / kTcTileM;
     const int n_stages = p.k_steps / 2;
     unsigned g = 0;  // stages produced so far by this CTA (buffer = g & 1, use count of that buffer = g >> 1)
+
+    // this thread's column of a tile and the 8 magnitudes of one stage (issued as 8 independent coalesced loads)
+    struct Col { bool ok; long long b; int t; const float *src; };
+    auto locate = [&](long long tile) {
+        Col c;
+        const long long col = tile * kTcTileM + fi;
+        c.ok = tile < n_tiles && col < p.n_cols;
+        c.b = c.ok ? col / p.T : 0;
+        c.t = c.ok ? (int)(col - c.b * p.T) : 0;
+        c.src = p.mag + (c.b * p.F) * (long long)p.T + c.t;
+        return c;
+    };
+    auto fetch = [&](const Col &c, int s, float *v) {
+        const int k0 = s * kTcStageBins + bg * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (c.ok && k0 + j < p.F) ? __ldg(c.src + (long long)(k0 + j) * p.T) : 0.f;
+    };
+
+    Col col = locate(blockIdx.x);
+    float v[8];
+    fetch(col, 0, v);  // software pipeline: the loads of stage s + 1 are in flight while stage s is converted and issued
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long c = tile * kTcTileM + fi;
-        const bool col_ok = c < p.n_cols;
-        const long long cb = col_ok ? c / p.T : 0;
-        const int ct = col_ok ? (int)(c - cb * p.T) : 0;
-        const float *src = p.mag + (cb * p.F) * (long long)p.T + ct;
+        const bool col_ok = col.ok;
+        const long long cb = col.b;
+        const int ct = col.t;
+        const Col next_col = locate(tile + gridDim.x);
 
         for (int s = 0; s < n_stages; ++s, ++g) {
             const unsigned buf = g & 1u, use = g >> 1;
-            if (use > 0) mbar_wait(smem_u32(s_bar + buf), (use - 1) & 1u);  // the MMAs that read this buffer are done
-            // ---- produce: 8 coalesced loads (one bin row each), fp32 -> bf16 hi / lo, MN-major stores
-            const int k0 = s * kTcStageBins + bg * 8;
-            float v[8];
+            // ---- produce: fp32 -> bf16 hi / lo, MN-major stores
+            __nv_bfloat16 h[8], l[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = (col_ok && k0 + j < p.F) ? __ldg(src + (long long)(k0 + j) * p.T) : 0.f;
+            for (int j = 0; j < 8; ++j) {
+                h[j] = __float2bfloat16_rn(v[j]);
+                l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h[j]));
+            }
+            if (s + 1 < n_stages) fetch(col, s + 1, v);
+            else fetch(next_col, 0, v);
+            if (use > 0) mbar_wait(smem_u32(s_bar + buf), (use - 1) & 1u);  // the MMAs that read this buffer are done
             unsigned char *dst = a_dst0 + buf * kTcABuf;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
-                const __nv_bfloat16 l = __float2bfloat16_rn(v[j] - __bfloat162float(h));
-                *reinterpret_cast<__nv_bfloat16 *>(dst + j * 16) = h;
-                *reinterpret_cast<__nv_bfloat16 *>(dst + kTcALimb + j * 16) = l;
+                *reinterpret_cast<__nv_bfloat16 *>(dst + j * 16) = h[j];
+                *reinterpret_cast<__nv_bfloat16 *>(dst + kTcALimb + j * 16) = l[j];
             }
             fence_proxy_async();
             __syncthreads();
@@ -194,6 +216,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mel_tc_kernel(const TcParams p)
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();  // the accumulator may be overwritten by the next tile's first MMA
         }
+        col = next_col;
     }
     // ---- teardown
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

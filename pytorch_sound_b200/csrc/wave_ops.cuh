@@ -133,12 +133,39 @@ __global__ void stft_loss_final_kernel(const double *acc, long long B, long long
 struct PullArgs {
     const float *peer[16];      // peer[r] = rank r's symmetric buffer as mapped in this process (peer[rank] unused)
     long long off[17];          // element offset of block r in every buffer; off[world] = total elements
+    int *peer_sync[16];         // peer_sync[r] = rank r's sync words as mapped here: [0, world) arrival flags, [world] epoch,
+                                // [world + 1] ticket; null = the caller orders the ranks itself
     int world, rank;
+    int pull;                   // 0: barrier only (the copies are done by the copy engines, b200mel_gather_copy)
 };
+// The cross-rank barrier lives INSIDE the kernel (no separate barrier launch, CUDA-graph replayable): the step
+// number is epoch + 1, where the epoch word is advanced by the last CTA of every launch — so it is the same for
+// every CTA of a launch and for the matching launches of all ranks, and a replayed graph keeps counting.  Block
+// 0 publishes "my block of this step is written" (the extraction kernel precedes this launch in stream order) to
+// every peer with a system-scope release store; every CTA then spins (bounded, then traps) with system-scope
+// acquire loads on its OWN rank's flags until all peers have published this step.
 __global__ void __launch_bounds__(512) gather_pull_kernel(float *__restrict__ local, const PullArgs a) {
+    int *sync = a.peer_sync[a.rank];
+    __shared__ int s_step;
+    if (sync) {
+        if (threadIdx.x == 0) s_step = *reinterpret_cast<volatile int *>(sync + a.world) + 1;
+        __syncthreads();
+        const int step = s_step;
+        const int r = threadIdx.x;
+        if (r < a.world && r != a.rank) {
+            if (blockIdx.x == 0) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(a.peer_sync[r] + a.rank), "r"(step) : "memory");
+            int seen;
+            unsigned spins = 0;
+            do {
+                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(sync + r) : "memory");
+                if (seen - step < 0 && ++spins > (1u << 26)) __trap();  // a peer never arrived: CUDA error, not a hung GPU
+            } while (seen - step < 0);
+        }
+        __syncthreads();
+    }
     const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long nthreads = (long long)gridDim.x * blockDim.x;
-    for (int i = 1; i < a.world; ++i) {
+    for (int i = 1; i < (a.pull ? a.world : 1); ++i) {
         const int r = (a.rank + i) % a.world;  // stagger the peers: at any moment the ranks read from different GPUs
         const long long lo = a.off[r], hi = a.off[r + 1];
         const float *src = a.peer[r];
@@ -170,9 +197,56 @@ __global__ void __launch_bounds__(512) gather_pull_kernel(float *__restrict__ lo
             d4[k] = v;
         }
     }
+    if (sync) {  // the last CTA of the launch advances the epoch
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const int t = atomicAdd(sync + a.world + 1, 1);
+            if (t == (int)gridDim.x - 1) {
+                sync[a.world + 1] = 0;
+                __threadfence();
+                *reinterpret_cast<volatile int *>(sync + a.world) = s_step;
+            }
+        }
+    }
 }
 
-// mel (B, M, T) -> mfcc (B, C, T).  A warp owns 32 consecutive (b, t) columns (every global access a contiguous
+// mel (B, M, T) -> mfcc (B, C, T), DCT matrix in CONSTANT memory.  A thread owns one (b, t) column: its M mel values
+// are read once into registers (a warp reads 32 consecutive frames of a mel row: full 128-byte lines) and every
+// output row is M FFMAs whose weight operand comes straight from the constant bank — warp-uniform, so it costs no
+// load instruction and no shared-memory wavefront (the shared-memory variant below is bound by exactly those:
+// 25.5 us at C2 against 3.6 us here; the HBM time of 10.7 MB is 1.6 us).  Rows of the matrix are kM floats apart.
+constexpr int kDctConstRows = 64, kDctConstCols = 128;
+__constant__ float c_dct[kDctConstRows * kDctConstCols];
+template <int kM>
+__global__ void __launch_bounds__(128) dct_const_kernel(const float *__restrict__ mel, float *__restrict__ out, long long B,
+                                                         int C, int T) {
+    const long long cols = B * (long long)T;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cols; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / T;
+        const int t = (int)(i - b * T);
+        const float *src = mel + (b * kM) * (long long)T + t;
+        float *dst = out + (b * C) * (long long)T + t;
+        float v[kM];
+#pragma unroll
+        for (int m = 0; m < kM; ++m) v[m] = src[(long long)m * T];
+#pragma unroll 2
+        for (int c = 0; c < C; ++c) {
+            const float *w = c_dct + c * kM;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four chains, summed as the shared-memory kernel does
+#pragma unroll
+            for (int m = 0; m + 3 < kM; m += 4) {
+                a0 = fmaf(w[m], v[m], a0);
+                a1 = fmaf(w[m + 1], v[m + 1], a1);
+                a2 = fmaf(w[m + 2], v[m + 2], a2);
+                a3 = fmaf(w[m + 3], v[m + 3], a3);
+            }
+            dst[(long long)c * T] = (a0 + a1) + (a2 + a3);
+        }
+    }
+}
+
+// mel (B, M, T) -> mfcc (B, C, T), general shapes.  A warp owns 32 consecutive (b, t) columns (every global access a contiguous
 // 128-byte line) and kDctRows output rows: the column's M mel values are read into registers once per warp (the
 // C / kDctRows warps that share a column block re-read them from L1/L2, the mel tensor is small), and the DCT rows
 // come from shared memory (rows padded to a multiple of 4) as 128-bit warp-wide broadcasts, one LDS.128 per 4 FFMAs.

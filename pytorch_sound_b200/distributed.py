@@ -7,10 +7,11 @@ Two gathers:
 
   mode="nccl"   `dist.all_gather_into_tensor` (NCCL over NVLink / NVSwitch); works on any backend (gloo in the CPU tests).
   mode="fused"  the extraction kernel writes the rank's block straight into its slot of a SYMMETRIC buffer
-                (torch.distributed._symmetric_memory: the same allocation on every rank, peer-mapped), a device-side
-                barrier on the signal pads orders the ranks, and one pull kernel (b200mel_gather_pull: 16-byte loads
-                from the peers' buffers over NVLink) completes the local copy — no NCCL call, no host
-                synchronisation, no staging copy of the local block, and the result IS the symmetric buffer.
+                (torch.distributed._symmetric_memory: the same allocation on every rank, peer-mapped) and ONE more
+                kernel finishes the step (b200mel_gather_pull): it runs the cross-rank barrier itself (system-scope
+                release / acquire flags in symmetric memory) and then pulls the peers' blocks with 16-byte loads
+                over NVLink — no NCCL call, no host synchronisation, no staging copy of the local block, CUDA-graph
+                replayable, and the result IS the symmetric buffer.
                 Three buffers rotate: a rank may only overwrite its block of a buffer once every peer has pulled
                 it, which its own NEXT barrier implies — so the extraction of step i is ordered after the gather of
                 step i-2 (automatic on one stream; with a separate communication stream wait on that gather's
@@ -73,8 +74,15 @@ class SymmetricGather:
 
     N_SLOTS = 3
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, engine: str = "pull"):
+        """engine="pull": SM kernel with 16-byte peer loads (fastest when the gather runs alone);
+        engine="copy": one-CTA barrier kernel + copy-engine transfers (overlaps with an extraction kernel that fills
+        the SMs on another stream)."""
         import torch.distributed._symmetric_memory as symm_mem
+
+        if engine not in ("pull", "copy"):
+            raise ValueError("engine must be 'pull' or 'copy'")
+        self.engine = engine
 
         self._symm = symm_mem
         self.group = group if group is not None else dist.group.WORLD
@@ -85,10 +93,20 @@ class SymmetricGather:
         self._capacity = 0
         self._step = 0
         self._shape = None
+        self._sync = None        # symmetric int32[world + 2]: arrival flags, epoch, ticket (gather_pull_kernel)
+        self._sync_hdl = None
+        self._call_args = {}     # ctypes argument blocks per (slot, shape): kept alive, reused across steps
 
     def _ensure(self, numel: int, device: torch.device) -> None:
+        if self._sync is None:
+            self._sync = self._symm.empty(self.world + 2, dtype=torch.int32, device=device)
+            self._sync.zero_()
+            self._sync_hdl = self._symm.rendezvous(self._sync, self.group)
+            torch.cuda.current_stream(device).synchronize()
+            self._sync_hdl.barrier(channel=0)  # every rank's sync words are zero before anyone signals
         if numel <= self._capacity:
             return
+        self._call_args = {}
         self._bufs, self._hdls = [], []
         for _ in range(self.N_SLOTS):
             t = self._symm.empty(numel, dtype=torch.float32, device=device)
@@ -103,6 +121,8 @@ class SymmetricGather:
         return self._bufs[self._step % self.N_SLOTS][:numel].view(n_clips, n_mels, n_frames)
 
     def finish(self) -> torch.Tensor:
+        """Enqueue the gather of the current slot on the current stream (ONE kernel: in-kernel barrier + peer pulls;
+        capturable in a CUDA graph) and return the slot, which holds every rank's rows once the kernel has run."""
         from . import _lib
 
         n_clips, n_mels, n_frames = self._shape
@@ -110,14 +130,18 @@ class SymmetricGather:
         buf, hdl = self._bufs[i], self._hdls[i]
         self._step += 1
         per_clip = n_mels * n_frames
-        offs = [shard_range(n_clips, r, self.world)[0] * per_clip for r in range(self.world)] + [n_clips * per_clip]
-        # every rank has written its block (stream-ordered on each rank; the barrier is device-side on the signal pads)
-        hdl.barrier(channel=0)
-        peers = (C.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
-        offs_c = (C.c_int64 * (self.world + 1))(*offs)
+        key = (i, self._shape)
+        args = self._call_args.get(key)
+        if args is None:
+            offs = [shard_range(n_clips, r, self.world)[0] * per_clip for r in range(self.world)] + [n_clips * per_clip]
+            args = ((C.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs]),
+                    (C.c_void_p * self.world)(*[int(p) for p in self._sync_hdl.buffer_ptrs]),
+                    (C.c_int64 * (self.world + 1))(*offs))
+            self._call_args[key] = args
         with torch.cuda.device(buf.device):
-            rc = _lib.lib().b200mel_gather_pull(buf.data_ptr(), peers, self.world, self.rank, offs_c,
-                                                C.c_void_p(torch.cuda.current_stream(buf.device).cuda_stream))
+            fn = _lib.lib().b200mel_gather_pull if self.engine == "pull" else _lib.lib().b200mel_gather_copy
+            rc = fn(buf.data_ptr(), args[0], args[1], self.world, self.rank, args[2],
+                    C.c_void_p(torch.cuda.current_stream(buf.device).cuda_stream))
         _lib.check(rc)
         return buf[:n_clips * per_clip].view(n_clips, n_mels, n_frames)
 
