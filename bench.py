@@ -476,11 +476,13 @@ def main():
             try:
                 sg = SymmetricGather(engine=engine)
 
-                def fused_launch(i):
-                    full = sg.slot(world * B_PER_GPU, N_MELS, T, dev)
-                    module(d_in[i % NBUF], out=full[a0:a0 + B_PER_GPU])
+                spare = 1 if engine == "copy" else 0  # one SM for the barrier CTA that gates the copy-engine transfers
 
-                def fused_collect(i):
+                def fused_launch(i, spare=spare, sg=sg):
+                    full = sg.slot(world * B_PER_GPU, N_MELS, T, dev)
+                    module(d_in[i % NBUF], out=full[a0:a0 + B_PER_GPU], reserve_sms=spare)
+
+                def fused_collect(i, sg=sg):
                     sg.finish()
 
                 pipeline(6, fused_launch, fused_collect)  # eager warm-up (allocates + rendezvous), ends on slot 0

@@ -161,6 +161,11 @@ typedef struct b200mel_io {
     const int32_t *lengths;
     float *out_mel, *out_a, *out_b;
     float *out_frame_mask;
+    int32_t reserve_sms; /* the persistent mel kernel launches on (SM count - reserve_sms) SMs (0 = all).  It owns every
+                            register of an SM it runs on, so a concurrent kernel on another stream — e.g. the one-CTA
+                            barrier of b200mel_gather_copy, which gates the copy-engine transfers — only gets an SM
+                            when one is left free. */
+    int32_t reserved_;   /* 0 */
 } b200mel_io;
 int b200mel_forward_io(const b200mel_plan *plan, const b200mel_io *io, const b200mel_epilogue *epi, void *stream);
 

@@ -132,8 +132,11 @@ struct b200mel_plan {
     // shared-memory layout
     int off_window = 0, off_entries = 0, off_melw = 0, off_bar = 0, off_regions = 0, region_bytes = 0, stage_bytes = 0;
     int n_warps = 0, smem_bytes = 0;
-    // spectrum-output kernel (spec_kernel.cuh): tw | window | mbarriers | slots | 8 warp regions | tile A | tile B
-    int sp_off_bar = 0, sp_off_slots = 0, sp_off_regions = 0, sp_off_tiles = 0, sp_smem_bytes = 0;
+    // spectrum-output kernel (spec_kernel.cuh): tw | window | mbarriers | slots | warp regions | tile A | tile B;
+    // one layout per output kind (index = B200MEL_SPEC_*): |X| only runs 16 warps x 1 task, two outputs 8 warps x 2 tasks
+    struct SpecLayout {
+        int warps = 0, rt = 0, region = 0, off_bar = 0, off_slots = 0, off_regions = 0, off_tiles = 0, smem = 0;
+    } sp[4];
     // staging for forward_host: one (input, output) pair per CUDA stream that has called it, so calls on different
     // streams overlap (copy of one batch under the kernel / read-back of another); calls on one stream are ordered
     // by the stream itself.  Guarded by host_mu.
@@ -182,15 +185,31 @@ static int layout_smem(b200mel_plan *pl) {
         return fail(B200MEL_EUNSUP, "plan: hop_length / filterbank too large for the shared-memory staging of this build");
     pl->n_warps = n_warps;
     pl->smem_bytes = pl->off_regions + n_warps * pl->region_bytes;
-    // spectrum-output kernel
-    const int cols = pl->pair ? 2 * kSpecWarps : kSpecWarps;
-    pl->sp_off_bar = pl->off_window + n_fft * 4;
-    pl->sp_off_slots = pl->sp_off_bar + kSpecWarps * 8;
-    pl->sp_off_regions = (pl->sp_off_slots + kSpecWarps * (int)sizeof(SpecSlot) + 127) & ~127;
-    pl->sp_off_tiles = pl->sp_off_regions + kSpecWarps * pl->region_bytes;
-    pl->sp_smem_bytes = pl->sp_off_tiles + 2 * pl->phys_n_freq * (cols + 1) * 4;
-    if (pl->sp_smem_bytes > kMaxSmem)
-        return fail(B200MEL_EUNSUP, "plan: hop_length too large for the shared-memory staging of the spectrum kernel");
+    // spectrum-output kernel: per output kind the widest (warps x tasks-per-round) shape that fits in shared memory
+    const int sp_region = (std::max(kXposeBytes, pl->stage_bytes) + 127) & ~127;  // stage overlaid on the transpose buffer
+    for (int kind = 1; kind <= 3; ++kind) {
+        const int n_tiles = kind == B200MEL_SPEC_MAG ? 1 : 2;
+        static const int shapes[3][2] = {{16, 1}, {8, 2}, {8, 1}};
+        b200mel_plan::SpecLayout best;
+        for (const auto &sh : shapes) {
+            if (kind != B200MEL_SPEC_MAG && sh[0] == 16) continue;  // two tiles never fit next to 16 warp regions
+            b200mel_plan::SpecLayout L;
+            L.warps = sh[0], L.rt = sh[1], L.region = sp_region;
+            const int cols = L.warps * L.rt * (pl->pair ? 2 : 1);
+            L.off_bar = pl->off_window + n_fft * 4;
+            L.off_slots = L.off_bar + L.warps * 8;
+            L.off_regions = (L.off_slots + L.warps * L.rt * (int)sizeof(SpecSlot) + 127) & ~127;
+            L.off_tiles = L.off_regions + L.warps * L.region;
+            L.smem = L.off_tiles + n_tiles * pl->phys_n_freq * (cols + 1) * 4;
+            if (L.smem <= kMaxSmem) {
+                best = L;
+                break;
+            }
+        }
+        if (!best.warps)
+            return fail(B200MEL_EUNSUP, "plan: hop_length too large for the shared-memory staging of the spectrum kernel");
+        pl->sp[kind] = best;
+    }
     return B200MEL_OK;
 }
 
@@ -358,10 +377,19 @@ static kernel_fn pick_mel_kernel(bool pair, int power) {
 }
 static kernel_fn pick_kernel(bool pair, int spec, bool mel, int power, int top_groups) {
     if (mel) return top_groups == 12 ? pick_mel_kernel<12>(pair, power) : pick_mel_kernel<16>(pair, power);
+    (void)spec;
+    return nullptr;
+}
+template <bool kPair, int kSpec>
+static kernel_fn pick_spec_shape(int warps, int rt) {
+    if (warps == 16) return spec_kernel<kPair, kSpec, 16, 1>;
+    return rt == 2 ? spec_kernel<kPair, kSpec, 8, 2> : spec_kernel<kPair, kSpec, 8, 1>;
+}
+static kernel_fn pick_spec_kernel(bool pair, int spec, int warps, int rt) {
     switch (spec) {
-        case B200MEL_SPEC_MAG_PHASE: return pair ? spec_kernel<true, 1> : spec_kernel<false, 1>;
-        case B200MEL_SPEC_RE_IM: return pair ? spec_kernel<true, 2> : spec_kernel<false, 2>;
-        default: return pair ? spec_kernel<true, 3> : spec_kernel<false, 3>;
+        case B200MEL_SPEC_MAG_PHASE: return pair ? pick_spec_shape<true, 1>(warps, rt) : pick_spec_shape<false, 1>(warps, rt);
+        case B200MEL_SPEC_RE_IM: return pair ? pick_spec_shape<true, 2>(warps, rt) : pick_spec_shape<false, 2>(warps, rt);
+        default: return pair ? pick_spec_shape<true, 3>(warps, rt) : pick_spec_shape<false, 3>(warps, rt);
     }
 }
 
@@ -538,13 +566,12 @@ int b200mel_plan_create(const b200mel_config *cfg, b200mel_plan **out) {
             if (rc) break;
         } else if ((rc = layout_smem(pl)) != B200MEL_OK)
             break;
-        for (int spec = 0; spec <= 3 && e == cudaSuccess; ++spec)
-            for (int power = 1; power <= 2 && e == cudaSuccess; ++power) {
-                if (spec != 0 && power == 2) continue;
-                for (int top = 12; top <= (spec == 0 ? 16 : 12) && e == cudaSuccess; top += 4)
-                    e = cudaFuncSetAttribute(pick_kernel(pl->pair, spec, spec == 0, power, top),
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-            }
+        for (int power = 1; power <= 2 && e == cudaSuccess; ++power)
+            for (int top = 12; top <= 16 && e == cudaSuccess; top += 4)
+                e = cudaFuncSetAttribute(pick_kernel(pl->pair, 0, true, power, top), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        for (int spec = 1; spec <= 3 && e == cudaSuccess; ++spec)
+            e = cudaFuncSetAttribute(pick_spec_kernel(pl->pair, spec, pl->sp[spec].warps, pl->sp[spec].rt),
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         for (const FastEntry &fe : g_fast)
             if (e == cudaSuccess) e = cudaFuncSetAttribute(fe.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute (is the library built for this GPU?)"); break; }
@@ -606,6 +633,7 @@ int b200mel_forward_io(const b200mel_plan *pl, const b200mel_io *io, const b200m
     const int32_t *lengths = io->lengths;
     float *out_mel = io->out_mel, *out_a = io->out_a, *out_b = io->out_b;
     const int32_t spec_kind = io->spec_kind;
+    if (io->reserve_sms < 0) return fail(B200MEL_EINVAL, "forward: negative reserve_sms");
     if (io->out_frame_mask && pl->cfg.pad_mode != B200MEL_PAD_CENTER)
         return fail(B200MEL_EINVAL, "forward: out_frame_mask needs centre framing (SpectrogramMasker geometry)");
     if (io->out_frame_mask && !out_mel) return fail(B200MEL_EINVAL, "forward: out_frame_mask is written by the mel launch");
@@ -701,7 +729,9 @@ int b200mel_forward_io(const b200mel_plan *pl, const b200mel_io *io, const b200m
     p.tasks_per_clip = (int)tpc;
     p.n_tasks = tpc * B;
     long long n_cta = (p.n_tasks + pl->n_warps - 1) / pl->n_warps;
-    if (n_cta > pl->num_sms) n_cta = pl->num_sms;  // persistent: one CTA per SM, warps stride over the tasks
+    int usable_sms = pl->num_sms;
+    if (io->reserve_sms > 0) usable_sms = std::max(1, pl->num_sms - io->reserve_sms);
+    if (n_cta > usable_sms) n_cta = usable_sms;  // persistent: one CTA per SM, warps stride over the tasks
     const long long stride = n_cta * pl->n_warps;
     p.stride_b = (int)(stride / tpc);
     p.stride_q = (int)(stride % tpc);
@@ -729,20 +759,24 @@ int b200mel_forward_io(const b200mel_plan *pl, const b200mel_io *io, const b200m
         g_launches.fetch_add(1);
     }
     if (spec_kind && le == cudaSuccess) {
-        // cooperative 8-warp kernel with its own shared-memory carve-up and launch shape
-        long long s_cta = (p.n_tasks + kSpecWarps - 1) / kSpecWarps;
+        // cooperative kernel with its own shared-memory carve-up and launch shape (per output kind)
+        const b200mel_plan::SpecLayout &L = pl->sp[spec_kind];
+        const int round_tasks = L.warps * L.rt;
+        long long s_cta = (p.n_tasks + round_tasks - 1) / round_tasks;
         if (s_cta > pl->num_sms) s_cta = pl->num_sms;
-        const long long s_stride = s_cta * kSpecWarps;
-        p.stride_b = (int)(s_stride / tpc);
-        p.stride_q = (int)(s_stride % tpc);
-        p.off_bar = pl->sp_off_bar;
-        p.off_entries = pl->sp_off_slots;
-        p.off_regions = pl->sp_off_regions;
-        p.off_melw = pl->sp_off_tiles;
+        // a warp's jump from the last sub-task of a round to the first of its next round
+        const long long jump = s_cta * round_tasks - (long long)(L.rt - 1) * L.warps;
+        p.stride_b = (int)(jump / tpc);
+        p.stride_q = (int)(jump % tpc);
+        p.off_bar = L.off_bar;
+        p.off_entries = L.off_slots;
+        p.off_regions = L.off_regions;
+        p.off_melw = L.off_tiles;
+        p.region_bytes = L.region;
         cfg.gridDim = dim3((unsigned)s_cta);
-        cfg.blockDim = dim3(kSpecWarps * 32);
-        cfg.dynamicSmemBytes = pl->sp_smem_bytes;
-        le = cudaLaunchKernelEx(&cfg, pick_kernel(pl->pair, spec_kind, false, 1, kSpecWarps), p);
+        cfg.blockDim = dim3(L.warps * 32);
+        cfg.dynamicSmemBytes = L.smem;
+        le = cudaLaunchKernelEx(&cfg, pick_spec_kernel(pl->pair, spec_kind, L.warps, L.rt), p);
         g_launches.fetch_add(1);
     }
     if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx");

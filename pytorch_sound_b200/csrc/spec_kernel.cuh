@@ -15,9 +15,7 @@
 
 namespace b200mel {
 
-constexpr int kSpecWarps = 8;
-
-struct SpecSlot {  // where the columns of one warp's task go (written by lane 0 of the warp every round)
+struct SpecSlot {  // where the columns of one task go (written by lane 0 of the task's warp every round)
     long long row0;  // element offset of (clip b, bin 0, frame t0) in the output arrays
     int n_frames;    // valid frames of the task (0 = idle slot, 1, or 2 in pair mode)
     int zero;        // 1: the task lies past the clip's own end (lengths) -> its columns are written as zeros
@@ -55,13 +53,21 @@ __device__ __forceinline__ void spec_deposit(float *ta, float *tb, int idx, floa
     }
 }
 
-// Shared layout (bytes): tw 8192 | window 4 n_fft | mbarriers | slots | 8 warp regions | tile A | tile B
-template <bool kPair, int kSpec>
-__global__ void __launch_bounds__(kSpecWarps * 32, 1) spec_kernel(const KParams p) {
+// kWarps warps per CTA, each running kRT tasks per round; the CTA tile holds kWarps * kRT * (2 | 1) frame columns:
+//   |X| only (one tile):        16 warps x 1 task  -> 32 columns in pair mode: a warp stores 128 contiguous bytes of a row
+//   two outputs (two tiles):     8 warps x 2 tasks -> 32 columns too (the tiles leave room for 8 warp regions only)
+// Round = {every warp: kRT x (TMA stage -> window -> radix-32 -> transpose + twiddle -> radix-32 -> separation ->
+// deposit its columns)} -> __syncthreads -> cooperative row-wise write-out -> __syncthreads.
+// Shared layout (bytes): tw 8192 | window 4 n_fft | mbarriers | slots | warp regions | tile A | tile B.  A warp region
+// is the transpose buffer with the sample stage overlaid at offset 0 (the stage is consumed before the transpose is
+// written, and the next TMA is issued only after the transpose has been read back).
+template <bool kPair, int kSpec, int kWarps, int kRT>
+__global__ void __launch_bounds__(kWarps * 32, 1) spec_kernel(const KParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-    constexpr int kCols = kPair ? 2 * kSpecWarps : kSpecWarps;  // frame columns of the CTA tile
-    constexpr int kRowStride = kCols + 1;                      // odd stride: conflict-free deposits and row reads
+    constexpr int kFr = kPair ? 2 : 1;
+    constexpr int kCols = kWarps * kRT * kFr;  // frame columns of the CTA tile
+    constexpr int kRowStride = kCols + 1;      // odd stride: conflict-free deposits and row reads
     constexpr bool kTwo = kSpec != B200MEL_SPEC_MAG;
 
     float2 *s_tw = reinterpret_cast<float2 *>(smem_raw);
@@ -70,16 +76,26 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) spec_kernel(const KParams 
     SpecSlot *s_slot = reinterpret_cast<SpecSlot *>(smem_raw + p.off_entries);
     unsigned char *region = smem_raw + p.off_regions + warp * p.region_bytes;
     float2 *buf = reinterpret_cast<float2 *>(region);
-    float *stage = reinterpret_cast<float *>(region + kStageOff);
+    float *stage = reinterpret_cast<float *>(region);
     float *tile_a = reinterpret_cast<float *>(smem_raw + p.off_melw);
     float *tile_b = tile_a + p.n_freq * kRowStride;
     const uint32_t bar = smem_u32(s_bar + warp);
+    const uint32_t stage_s = smem_u32(stage);
     uint32_t parity = 0;
 
-    const long long stride = (long long)gridDim.x * kSpecWarps;
-    long long task = (long long)blockIdx.x * kSpecWarps + warp;
+    // task sequence of this warp: round r, sub-task s -> task (blockIdx + r gridDim) * kWarps * kRT + s * kWarps + warp
+    constexpr int kRoundTasks = kWarps * kRT;
+    const long long round_stride = (long long)gridDim.x * kRoundTasks;
+    long long task = (long long)blockIdx.x * kRoundTasks + warp;
     long long cb = task / p.tasks_per_clip;
     int cq = (int)(task - cb * p.tasks_per_clip);
+    const int sub_db = kWarps / p.tasks_per_clip, sub_dq = kWarps % p.tasks_per_clip;  // + kWarps tasks
+    // + (round_stride - (kRT - 1) kWarps) tasks: pre-split on the host as stride_b / stride_q
+    auto advance = [&](long long &b, int &q, int db, int dq) {
+        b += db;
+        q += dq;
+        if (q >= p.tasks_per_clip) q -= p.tasks_per_clip, ++b;
+    };
 
     if (lane == 0) {
         mbar_init(bar, 1);
@@ -90,7 +106,6 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) spec_kernel(const KParams 
     for (int i = tid; i < p.n_fft / 4; i += blockDim.x)
         reinterpret_cast<int4 *>(s_win)[i] = __ldg(reinterpret_cast<const int4 *>(p.window) + i);
     asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: caller memory is only touched below this line
-    const uint32_t stage_s = smem_u32(stage);
     if (lane == 0 && task < p.n_tasks) {
         const Task t = decode_task<kPair>(p, cb, cq);
         if (t.valid0) issue_copy(copy_geom(p, t.b, t.s_first, t.span, t.Li), stage_s, bar);
@@ -100,108 +115,110 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) spec_kernel(const KParams 
 
     float2 wl = make_float2(1.f, 0.f);
     if (!kPair) wl = __ldg(p.tw_post + lane);
+    const int partner = (32 - lane) & 31;
 
     // all warps of the CTA run the same number of rounds (idle warps still join the barriers)
-    for (long long base = (long long)blockIdx.x * kSpecWarps; base < p.n_tasks; base += stride, task += stride) {
-        const bool have = task < p.n_tasks;
-        Task t;
-        t.valid0 = t.valid1 = false;
-        if (have) {
-            t = decode_task<kPair>(p, cb, cq);
-            cb += p.stride_b;
-            cq += p.stride_q;
-            if (cq >= p.tasks_per_clip) cq -= p.tasks_per_clip, ++cb;
-        }
-        float2 a[32];
-        if (t.valid0) {
-            const CopyGeom g = copy_geom(p, t.b, t.s_first, t.span, t.Li);
-            const int delta = g.delta;
-            mbar_wait(bar, parity);
-            parity ^= 1;
-            if (g.patch) patch_stage(p, t.b, t.s_first, t.span, t.Li, g, stage, lane);
-            const float *x0 = stage + delta + lane;
-            if (kPair) {
-                const float *x1 = x0 + (t.valid1 ? p.hop : 0);
+    for (long long base = (long long)blockIdx.x * kRoundTasks; base < p.n_tasks; base += round_stride) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float w = s_win[32 * j + lane];
-                    a[j] = __fmul2_rn(make_float2(x0[32 * j], t.valid1 ? x1[32 * j] : 0.f), make_float2(w, w));
-                }
-            } else {
-                const float2 *w2 = reinterpret_cast<const float2 *>(s_win);
+        for (int sub = 0; sub < kRT; ++sub) {
+            const bool have = task < p.n_tasks;
+            Task t;
+            t.valid0 = t.valid1 = false;
+            t.b = 0, t.t0 = 0;
+            if (have) t = decode_task<kPair>(p, cb, cq);
+            // coordinates of this warp's next task
+            if (sub + 1 < kRT) task += kWarps, advance(cb, cq, sub_db, sub_dq);
+            else task += round_stride - (kRT - 1) * kWarps, advance(cb, cq, p.stride_b, p.stride_q);
+            float2 a[32];
+            if (t.valid0) {
+                const CopyGeom g = copy_geom(p, t.b, t.s_first, t.span, t.Li);
+                mbar_wait(bar, parity);
+                parity ^= 1;
+                if (g.patch) patch_stage(p, t.b, t.s_first, t.span, t.Li, g, stage, lane);
+                const float *x0 = stage + g.delta + lane;
+                if (kPair) {
+                    const float *x1 = x0 + (t.valid1 ? p.hop : 0);
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    a[j] = __fmul2_rn(make_float2(x0[64 * j + lane], x0[64 * j + lane + 1]), w2[32 * j + lane]);
-            }
-            fft32(a);
-            __syncwarp();
-            static_for<0, 32>([&](auto k1_) {
-                constexpr int k1 = decltype(k1_)::value;
-                buf[k1 * kBufStride + lane] = a[fft32_pos(k1)];
-            });
-            __syncwarp();
-            xpose_read_twiddle<16>(a, buf, s_tw, lane);
-            __syncwarp();
-        }
-        // prefetch this warp's next task (its task index is task + stride)
-        if (lane == 0 && task + stride < p.n_tasks) {
-            const Task n = decode_task<kPair>(p, cb, cq);
-            if (n.valid0) issue_copy(copy_geom(p, n.b, n.s_first, n.span, n.Li), stage_s, bar);
-        }
-        if (lane == 0) {
-            SpecSlot s;
-            s.n_frames = have ? (kPair && p.pair_frames == 2 ? (t.t0 + 1 < p.T ? 2 : 1) : 1) : 0;
-            s.zero = have && !t.valid0;
-            s.row0 = have ? (t.b * p.n_freq_out) * (long long)p.T + t.t0 : 0;
-            if (have && kPair && p.pair_frames == 2 && t.valid0 && !t.valid1 && t.t0 + 1 < p.T) s.zero = 2;  // second frame only
-            s_slot[warp] = s;
-        }
-        if (t.valid0) {
-            fft32(a);
-            const int partner = (32 - lane) & 31;
-            const int col = kPair ? 2 * warp : warp;
-            static_for<0, 16>([&](auto k2_) {
-                constexpr int k2 = decltype(k2_)::value;
-                const float2 A = a[fft32_pos(k2)];
-                const float2 g0 = a[fft32_pos((32 - k2) & 31)];
-                const float2 g1 = a[fft32_pos(31 - k2)];
-                float2 Bv;
-                Bv.x = __shfl_sync(0xffffffffu, lane == 0 ? g0.x : g1.x, partner);
-                Bv.y = __shfl_sync(0xffffffffu, lane == 0 ? g0.y : g1.y, partner);
-                const int k = lane + 32 * k2;
-                const float2 Bc = make_float2(Bv.x, -Bv.y);                     // conj(B): an operand sign pattern
-                const float2 E = __fadd2_rn(A, Bc);                             // frame t
-                const float2 D = __fadd2_rn(A, make_float2(-Bc.x, -Bc.y));
-                const float2 O = make_float2(D.y, -D.x);                        // frame t+1 = -i (A - conj(B))
-                if constexpr (kPair) {
-                    spec_deposit<kSpec>(tile_a, tile_b, k * kRowStride + col, E.x, E.y, p.mag_eps);
-                    spec_deposit<kSpec>(tile_a, tile_b, k * kRowStride + col + 1, O.x, O.y, p.mag_eps);
+                    for (int j = 0; j < 32; ++j) {
+                        const float w = s_win[32 * j + lane];
+                        a[j] = __fmul2_rn(make_float2(x0[32 * j], t.valid1 ? x1[32 * j] : 0.f), make_float2(w, w));
+                    }
                 } else {
-                    constexpr float w64c = TwConst::c64[k2], w64s = TwConst::s64[k2];
-                    const float2 P = cmul(O, cmul(wl, make_float2(w64c, w64s)));
-                    const float2 X0 = cadd(E, P), X1 = csub(E, P);
-                    spec_deposit<kSpec>(tile_a, tile_b, k * kRowStride + col, X0.x, X0.y, p.mag_eps);
-                    spec_deposit<kSpec>(tile_a, tile_b, (1024 - k) * kRowStride + col, X1.x, -X1.y, p.mag_eps);
+                    const float2 *w2 = reinterpret_cast<const float2 *>(s_win);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        a[j] = __fmul2_rn(make_float2(x0[64 * j + lane], x0[64 * j + lane + 1]), w2[32 * j + lane]);
                 }
-            });
+                fft32(a);
+                __syncwarp();  // the stage has been consumed by every lane: the transpose may overwrite it
+                static_for<0, 32>([&](auto k1_) {
+                    constexpr int k1 = decltype(k1_)::value;
+                    buf[k1 * kBufStride + lane] = a[fft32_pos(k1)];
+                });
+                __syncwarp();
+                xpose_read_twiddle<16>(a, buf, s_tw, lane);
+                __syncwarp();
+            }
+            // prefetch this warp's next task into the (now free) stage
+            if (lane == 0 && task < p.n_tasks) {
+                const Task n = decode_task<kPair>(p, cb, cq);
+                if (n.valid0) issue_copy(copy_geom(p, n.b, n.s_first, n.span, n.Li), stage_s, bar);
+            }
+            const int slot = sub * kWarps + warp;
             if (lane == 0) {
-                const float2 A = a[fft32_pos(16)];
-                if constexpr (kPair) {
-                    spec_deposit<kSpec>(tile_a, tile_b, 512 * kRowStride + col, 2.f * A.x, 0.f, p.mag_eps);
-                    spec_deposit<kSpec>(tile_a, tile_b, 512 * kRowStride + col + 1, 2.f * A.y, 0.f, p.mag_eps);
-                } else {
-                    spec_deposit<kSpec>(tile_a, tile_b, 512 * kRowStride + col, 2.f * A.x, -2.f * A.y, p.mag_eps);
+                SpecSlot s;
+                s.n_frames = have ? (kPair && p.pair_frames == 2 ? (t.t0 + 1 < p.T ? 2 : 1) : 1) : 0;
+                s.zero = have && !t.valid0;
+                s.row0 = have ? (t.b * p.n_freq_out) * (long long)p.T + t.t0 : 0;
+                if (have && kPair && p.pair_frames == 2 && t.valid0 && !t.valid1 && t.t0 + 1 < p.T) s.zero = 2;  // second frame only
+                s_slot[slot] = s;
+            }
+            if (t.valid0) {
+                fft32(a);
+                const int col = slot * kFr;
+                static_for<0, 16>([&](auto k2_) {
+                    constexpr int k2 = decltype(k2_)::value;
+                    const float2 A = a[fft32_pos(k2)];
+                    const float2 g0 = a[fft32_pos((32 - k2) & 31)];
+                    const float2 g1 = a[fft32_pos(31 - k2)];
+                    float2 Bv;
+                    Bv.x = __shfl_sync(0xffffffffu, lane == 0 ? g0.x : g1.x, partner);
+                    Bv.y = __shfl_sync(0xffffffffu, lane == 0 ? g0.y : g1.y, partner);
+                    const int k = lane + 32 * k2;
+                    const float2 Bc = make_float2(Bv.x, -Bv.y);                     // conj(B): an operand sign pattern
+                    const float2 E = __fadd2_rn(A, Bc);                             // frame t
+                    const float2 D = __fadd2_rn(A, make_float2(-Bc.x, -Bc.y));
+                    const float2 O = make_float2(D.y, -D.x);                        // frame t+1 = -i (A - conj(B))
+                    if constexpr (kPair) {
+                        spec_deposit<kSpec>(tile_a, tile_b, k * kRowStride + col, E.x, E.y, p.mag_eps);
+                        spec_deposit<kSpec>(tile_a, tile_b, k * kRowStride + col + 1, O.x, O.y, p.mag_eps);
+                    } else {
+                        constexpr float w64c = TwConst::c64[k2], w64s = TwConst::s64[k2];
+                        const float2 P = cmul(O, cmul(wl, make_float2(w64c, w64s)));
+                        const float2 X0 = cadd(E, P), X1 = csub(E, P);
+                        spec_deposit<kSpec>(tile_a, tile_b, k * kRowStride + col, X0.x, X0.y, p.mag_eps);
+                        spec_deposit<kSpec>(tile_a, tile_b, (1024 - k) * kRowStride + col, X1.x, -X1.y, p.mag_eps);
+                    }
+                });
+                if (lane == 0) {
+                    const float2 A = a[fft32_pos(16)];
+                    if constexpr (kPair) {
+                        spec_deposit<kSpec>(tile_a, tile_b, 512 * kRowStride + col, 2.f * A.x, 0.f, p.mag_eps);
+                        spec_deposit<kSpec>(tile_a, tile_b, 512 * kRowStride + col + 1, 2.f * A.y, 0.f, p.mag_eps);
+                    } else {
+                        spec_deposit<kSpec>(tile_a, tile_b, 512 * kRowStride + col, 2.f * A.x, -2.f * A.y, p.mag_eps);
+                    }
                 }
             }
         }
-        __syncthreads();  // every warp's columns (and slot records) are in the tile
+        __syncthreads();  // every task's columns (and slot records) are in the tile
 
         // ------------------------------------------------------------------ cooperative row-wise write-out
         {
             const int col = tid % kCols, r0 = tid / kCols;
-            constexpr int kRowsPerPass = kSpecWarps * 32 / kCols;
-            const SpecSlot s = s_slot[kPair ? col >> 1 : col];
-            const int f = kPair ? col & 1 : 0;
+            constexpr int kRowsPerPass = kWarps * 32 / kCols;
+            const SpecSlot s = s_slot[col / kFr];
+            const int f = col % kFr;
             if (f < s.n_frames) {
                 const bool zero = s.zero == 1 || (s.zero == 2 && f == 1);
                 const long long off = s.row0 + f;

@@ -47,6 +47,26 @@ def test_struct_layouts_match_header(built_lib):
     assert re.findall(r"\b(?:int32_t|float)\s+(\w+);", epi_fields) == [f[0] for f in built_lib.Epilogue._fields_]
 
 
+def test_io_struct_matches_header(built_lib):
+    hdr = open(HEADER).read()
+    body = re.search(r"typedef struct b200mel_io \{(.*?)\} b200mel_io;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        decl = re.sub(r"^(const\s+)?(float|int32_t|int64_t)\s*", "", decl)
+        names += [n.strip().lstrip("*").strip() for n in decl.split(",")]
+    assert names == [f[0] for f in built_lib.IO._fields_]
+    # pointers / int64 are 8-byte aligned: 2 x int32, then 9 x 8 bytes, then 2 x int32
+    assert C.sizeof(built_lib.IO) == 8 + 9 * 8 + 8
+    lib = built_lib.lib()
+    io = built_lib.IO()
+    io.struct_size = 4
+    assert lib.b200mel_forward_io(None, C.byref(io), None, None) == built_lib.EINVAL
+
+
 def test_error_codes_without_gpu(built_lib):
     import torch
 
