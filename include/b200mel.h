@@ -152,7 +152,7 @@ int b200mel_forward(const b200mel_plan *plan, const float *wav, int64_t B, int64
  *                   t*hop - win_length/2 < lengths[b] (all ones without `lengths`).  Written by the same launch
  *                   as the mel frames (centre framing only).
  * b200mel_forward(plan, wav, B, L, row_stride, lengths, epi, out_mel, spec_kind, out_a, out_b, stream) is exactly
- * b200mel_forward_io with out_frame_mask = NULL. */
+ * b200mel_forward_io with out_frame_mask = NULL, reserve_sms = 0, preemphasis = 0. */
 typedef struct b200mel_io {
     int32_t struct_size; /* = sizeof(b200mel_io) */
     int32_t spec_kind;   /* B200MEL_SPEC_* */
@@ -165,7 +165,9 @@ typedef struct b200mel_io {
                             register of an SM it runs on, so a concurrent kernel on another stream — e.g. the one-CTA
                             barrier of b200mel_gather_copy, which gates the copy-engine transfers — only gets an SM
                             when one is left free. */
-    int32_t reserved_;   /* 0 */
+    float preemphasis;   /* != 0: y[n] = x[n] - preemphasis * x[n-1] with the reference's 1-sample reflect pad (y[0] = x[0] -
+                            preemphasis * x[1]) applied to the samples as they are staged, before framing — PreEmphasis.forward
+                            (models/sound.py:66-81) fused as a prologue of the mel launch */
 } b200mel_io;
 int b200mel_forward_io(const b200mel_plan *plan, const b200mel_io *io, const b200mel_epilogue *epi, void *stream);
 

@@ -38,7 +38,7 @@ class IO(C.Structure):
     _fields_ = [
         ("struct_size", C.c_int32), ("spec_kind", C.c_int32), ("wav", C.c_void_p), ("B", C.c_int64), ("L", C.c_int64),
         ("row_stride", C.c_int64), ("lengths", C.c_void_p), ("out_mel", C.c_void_p), ("out_a", C.c_void_p),
-        ("out_b", C.c_void_p), ("out_frame_mask", C.c_void_p), ("reserve_sms", C.c_int32), ("reserved_", C.c_int32),
+        ("out_b", C.c_void_p), ("out_frame_mask", C.c_void_p), ("reserve_sms", C.c_int32), ("preemphasis", C.c_float),
     ]
 
 

@@ -634,6 +634,10 @@ int b200mel_forward_io(const b200mel_plan *pl, const b200mel_io *io, const b200m
     float *out_mel = io->out_mel, *out_a = io->out_a, *out_b = io->out_b;
     const int32_t spec_kind = io->spec_kind;
     if (io->reserve_sms < 0) return fail(B200MEL_EINVAL, "forward: negative reserve_sms");
+    if (io->preemphasis != 0.f && (!io->out_mel || io->spec_kind))
+        return fail(B200MEL_EINVAL, "forward: fused pre-emphasis is a prologue of the mel launch (no spectrum outputs)");
+    if (io->preemphasis != 0.f && io->L < 2)
+        return fail(B200MEL_EINVAL, "forward: pre-emphasis needs L >= 2 (reflect pad, models/sound.py:80)");
     if (io->out_frame_mask && pl->cfg.pad_mode != B200MEL_PAD_CENTER)
         return fail(B200MEL_EINVAL, "forward: out_frame_mask needs centre framing (SpectrogramMasker geometry)");
     if (io->out_frame_mask && !out_mel) return fail(B200MEL_EINVAL, "forward: out_frame_mask is written by the mel launch");
@@ -703,6 +707,7 @@ int b200mel_forward_io(const b200mel_plan *pl, const b200mel_io *io, const b200m
     p.stage_bytes = pl->stage_bytes;
     p.out_mel = out_mel;
     p.out_fmask = io->out_frame_mask;
+    p.preemph = io->preemphasis;
     p.win_half = pl->cfg.win_length / 2;
     p.out_a = out_a;
     p.out_b = out_b;
@@ -753,7 +758,7 @@ int b200mel_forward_io(const b200mel_plan *pl, const b200mel_io *io, const b200m
     if (out_mel) {
         cfg.gridDim = dim3((unsigned)n_cta);
         cfg.blockDim = dim3(pl->n_warps * 32);
-        kernel_fn fn = (!lengths && p.use_log && !p.out_fmask) ? pick_fast_kernel(pl) : nullptr;
+        kernel_fn fn = (!lengths && p.use_log && !p.out_fmask && p.preemph == 0.f) ? pick_fast_kernel(pl) : nullptr;
         if (!fn) fn = pick_kernel(pl->pair, 0, true, pl->cfg.power, pl->top_groups);
         le = cudaLaunchKernelEx(&cfg, fn, p);
         g_launches.fetch_add(1);

@@ -105,6 +105,8 @@ struct KParams {
     int off_window, off_entries, off_melw, off_bar, off_regions, region_bytes, stage_bytes;
     // outputs
     float *out_mel, *out_a, *out_b;
+    float preemph;     // != 0: pre-emphasis y[n] = x[n] - preemph x[n-1] (y[0] = x[0] - preemph x[1]) applied to the staged
+                       // samples before framing (PreEmphasis.forward, models/sound.py:66-81), generic mel kernel only
     float *out_fmask;  // nullable (B, T): SpectrogramMasker frame mask, 1 iff t * hop - win_half < clip length
     int win_half;
     long long *dbg;  // phase-timing accumulators (debug builds only)
@@ -250,19 +252,51 @@ __device__ __forceinline__ CopyGeom copy_geom(const KParams &p, long long b, int
 // tasks per 1-s clip) and the floats dropped by the tensor-edge clamp.  The source sample is almost always
 // inside the staged part, so it is copied within shared memory; only a reflection that leaves the staged span
 // (or a clamped float) falls back to global memory.
+// sample r of a row as the FFT sees it: the raw sample, or the pre-emphasised one (same fmaf as preemph_kernel)
+__device__ __forceinline__ float row_sample(const float *row, int r, float preemph) {
+    const float v = __ldg(row + r);
+    return preemph != 0.f ? fmaf(-preemph, __ldg(row + (r > 0 ? r - 1 : 1)), v) : v;
+}
 __device__ __forceinline__ void patch_stage(const KParams &p, long long b, int s_first, int span, int Li,
-                                            const CopyGeom &g, float *stage, int lane) {
+                                            const CopyGeom &g, float *stage, int lane, float preemph = 0.f) {
     const float *row = p.wav + b * p.row_stride;
     float *st = stage + g.delta - s_first;  // st[s] = sample at padded-coordinate position s
     for (int s = s_first + lane; s < g.c_lo; s += 32) {
         const int r = reflect_index(s, Li);
-        st[s] = (r >= g.c_lo && r < g.c_hi) ? st[r] : __ldg(row + r);
+        st[s] = (r >= g.c_lo && r < g.c_hi) ? st[r] : row_sample(row, r, preemph);
     }
     for (int s = g.c_hi + lane; s < s_first + span; s += 32) {
         const int r = reflect_index(s, Li);
-        st[s] = (r >= g.c_lo && r < g.c_hi) ? st[r] : __ldg(row + r);
+        st[s] = (r >= g.c_lo && r < g.c_hi) ? st[r] : row_sample(row, r, preemph);
     }
     __syncwarp();
+}
+// Fused pre-emphasis (PreEmphasis.forward, models/sound.py:66-81, as a prologue of the extraction): the staged samples
+// [c_lo, c_hi) are replaced in place by y[s] = x[s] - c x[s-1] (y[0] = x[0] - c x[1], the reference's 1-sample reflect
+// pad) BEFORE the halo patch, so the reflected halo mirrors the pre-emphasised signal as F.pad of the reference's
+// output would.  Chunks of 256 samples are processed from the top down: a chunk reads its samples and the one just
+// below it (still raw — lower chunks come later) into registers, then writes.  Out of line: its registers must not
+// weigh on the allocation of the FFT loop it is called from.
+__device__ __noinline__ void preemphasize_stage(const float *row, float *st, int c_lo, int c_hi, float coef, int lane) {
+    const int n = c_hi - c_lo;
+    for (int base = ((n - 1) >> 8) << 8; base >= 0; base -= 256) {
+        float cur[8], prev[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int s = c_lo + base + 32 * i + lane;
+            if (s < c_hi) {
+                cur[i] = st[s];
+                prev[i] = s > c_lo ? st[s - 1] : __ldg(row + (s > 0 ? s - 1 : 1));
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int s = c_lo + base + 32 * i + lane;
+            if (s < c_hi) st[s] = fmaf(-coef, prev[i], cur[i]);
+        }
+        __syncwarp();
+    }
 }
 __device__ __forceinline__ void issue_copy(const CopyGeom &g, uint32_t stage_s, uint32_t bar) {
     fence_proxy_async();
@@ -420,7 +454,10 @@ __device__ __forceinline__ Desc request_task(const KParams &p, int b, int q, int
 __device__ __forceinline__ void patch_halo_smem(const KParams &p, const Desc &d, float *stage, int lane) {
     const int s_first = d.t0 * p.hop - p.pad;
     const int span = p.n_fft + ((d.flags & 2u) ? p.hop : 0);
-    patch_stage(p, d.b, s_first, span, d.Li, copy_geom(p, d.b, s_first, span, d.Li), stage, lane);
+    const CopyGeom g = copy_geom(p, d.b, s_first, span, d.Li);
+    if (p.preemph != 0.f && g.c_hi > g.c_lo)  // warp-uniform
+        preemphasize_stage(p.wav + (long long)d.b * p.row_stride, stage + g.delta - s_first, g.c_lo, g.c_hi, p.preemph, lane);
+    if (g.patch) patch_stage(p, d.b, s_first, span, d.Li, g, stage, lane, p.preemph);
 }
 
 // Pair mode, stage -> registers with the window applied: a[j] = {x_t[32 j + lane], x_t+1[32 j + lane]} * w[32 j + lane].
@@ -604,7 +641,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
             mbar_wait(bar, parity);
 #endif
             parity ^= 1;
-            if (d.flags & 4u) patch_halo(d);
+            if ((d.flags & 4u) || p.preemph != 0.f) patch_halo(d);
             const float *x0 = stage + d.delta + lane;
             PHASE_MARK(2);  // wait for the TMA stage
             if constexpr (kPair) {

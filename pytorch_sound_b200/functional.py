@@ -30,13 +30,14 @@ def _check_wav(wav: torch.Tensor) -> torch.Tensor:
 
 def run(plan: "_lib.Plan", wav: torch.Tensor, epi: Optional["_lib.Epilogue"], want_mel: bool = True,
         spec_kind: int = _lib.SPEC_NONE, lengths: Optional[torch.Tensor] = None,
-        out: Optional[torch.Tensor] = None, frame_mask: Optional[torch.Tensor] = None, reserve_sms: int = 0
-        ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
+        out: Optional[torch.Tensor] = None, frame_mask: Optional[torch.Tensor] = None, reserve_sms: int = 0,
+        preemphasis: float = 0.0) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
     """Launch the fused kernel on wav's device / current stream. Returns (mel, out_a, out_b).
 
     `out`: optional preallocated contiguous (B, n_mels, T) float32 CUDA tensor for the mel frames (e.g. a slice of a
     symmetric-memory gather buffer).  `frame_mask`: optional (B, T) float32 tensor the same launch fills with the
-    SpectrogramMasker frame mask.  `reserve_sms`: SMs the persistent mel kernel leaves free for concurrent kernels."""
+    SpectrogramMasker frame mask.  `reserve_sms`: SMs the persistent mel kernel leaves free for concurrent kernels.
+    `preemphasis`: coefficient of the fused pre-emphasis prologue (0 = off)."""
     wav = _check_wav(wav)
     dev = wav.device
     if dev.index != plan.device_index:
@@ -72,7 +73,7 @@ def run(plan: "_lib.Plan", wav: torch.Tensor, epi: Optional["_lib.Epilogue"], wa
         io = _lib.IO(C.sizeof(_lib.IO), spec_kind, wav.data_ptr(), B, L, wav.stride(0) if B > 1 else max(L, 1), len_ptr,
                      mel.data_ptr() if mel is not None else None, out_a.data_ptr() if out_a is not None else None,
                      out_b.data_ptr() if out_b is not None else None,
-                     frame_mask.data_ptr() if frame_mask is not None else None, int(reserve_sms), 0)
+                     frame_mask.data_ptr() if frame_mask is not None else None, int(reserve_sms), float(preemphasis))
         rc = _lib.lib().b200mel_forward_io(plan.handle, C.byref(io), C.byref(epi) if epi is not None else None,
                                            C.c_void_p(stream))
     _lib.check(rc)

@@ -158,18 +158,21 @@ class LogMelSpectrogram(_PlanUser):
                                  n_mels=mel_size, fmin=mel_min, fmax=mel_max, pad_mode=_lib.PAD_CENTER)
 
     def forward(self, wav: torch.Tensor, log_offset: float = 1e-6, lengths: Optional[torch.Tensor] = None,
-                norm: bool = False, frame_mask: bool = False, out: Optional[torch.Tensor] = None, reserve_sms: int = 0):
+                norm: bool = False, frame_mask: bool = False, out: Optional[torch.Tensor] = None, reserve_sms: int = 0,
+                preemphasis: float = 0.0):
         """`lengths` (int32 (B,), optional, extension): true clip lengths of a zero-padded batch — reflect at
         each clip's own end and zero the frames past it.  `norm=True` (extension) fuses utils.calculate.norm_mel.
         `frame_mask=True` (extension) also returns the (B, T) SpectrogramMasker frame mask (transforms.py:397-416),
         written by the same launch.  `out` (extension): preallocated (B, mel_size, T) tensor to write into.
-        `reserve_sms` (extension): SMs left free for a concurrent kernel on another stream (distributed.py)."""
+        `reserve_sms` (extension): SMs left free for a concurrent kernel on another stream (distributed.py).
+        `preemphasis` (extension): coefficient of models.sound.PreEmphasis (models/sound.py:66-81) fused into the launch —
+        equal to `LogMelSpectrogram(PreEmphasis(coef)(wav[:, None])[:, 0])` without the extra pass over the waveform."""
         epi = _lib.make_epilogue(_lib.LOG_LN_OFFSET, log_offset, self.min_db, self.max_db, norm)
         fm = None
         if frame_mask:
             fm = torch.empty((wav.shape[0], 1 + wav.shape[1] // self.stft.hop_length), device=wav.device, dtype=torch.float32)
         mel, _, _ = functional.run(self._plan(wav.device), wav, epi, lengths=lengths, out=out, frame_mask=fm,
-                                   reserve_sms=reserve_sms)
+                                   reserve_sms=reserve_sms, preemphasis=preemphasis)
         return (mel, fm) if frame_mask else mel
 
 

@@ -191,3 +191,44 @@ def test_logmelscale_tcgen05_vs_oracle(torch_cuda):
     # a filterbank whose bf16 limbs do not fit in shared memory next to the pipeline buffers: loud, no fallback
     with pytest.raises(ValueError, match="too large"):
         T.LogMelScale(22050, 128, 1024, -50, 30, 0.0, None).cuda()(torch.rand(1, 513, 4, device="cuda"))
+
+
+def test_fused_preemphasis_prologue(torch_cuda):
+    """LogMelSpectrogram(..., preemphasis=c): models.sound.PreEmphasis (models/sound.py:66-81) applied while the samples
+    are staged.  Same fmaf as the standalone kernel and the same extraction kernel afterwards, so it is BIT-equal to
+    PreEmphasis -> LogMelSpectrogram, including reflected edge frames, per-clip lengths and misaligned rows; and it
+    is within tolerance of the float64 oracle chain."""
+    torch = torch_cuda
+    from pytorch_sound_b200.models import transforms as T
+    from pytorch_sound_b200.models.sound import PreEmphasis
+
+    for geo, L in ((GEO, 22050), (GEO, 1500), (dict(sample_rate=44100, mel_size=128, n_fft=2048, win_length=2048, hop_length=512), 9000),
+                   (dict(GEO, hop_length=300), 5000)):
+        B = 5
+        x = cuda(torch, mo.synth_clips(B, L, geo["sample_rate"], seed=5 + L))
+        lm = T.LogMelSpectrogram(**geo).cuda()
+        full = torch.full((B,), L, device="cuda", dtype=torch.int32)
+        pre = PreEmphasis(0.97).cuda()(x.unsqueeze(1))[:, 0]
+        two_pass = lm(pre, lengths=full)             # generic kernel on the pre-emphasised waveform
+        fused = lm(x, lengths=full, preemphasis=0.97)
+        assert torch.equal(fused, two_pass), (geo, L)
+        assert float((lm(x, preemphasis=0.97) - fused).abs().max()) == 0.0  # without lengths: same generic kernel
+        ref = mo.log_mel_spectrogram(mo.pre_emphasis(x.cpu().numpy()[:, None, :], 0.97)[:, 0], **geo, clamp=False)
+        assert mo.parity_error(fused.cpu().numpy(), ref) < TOL
+    # ragged lengths: each clip is pre-emphasised and reflected within its own length
+    lens = [6000, 4500, 5999, 700]
+    x = torch.zeros(4, 6000, device="cuda")
+    clips = [mo.synth_clips(1, n, 22050, seed=40 + i)[0] for i, n in enumerate(lens)]
+    for i, c in enumerate(clips):
+        x[i, :len(c)] = torch.from_numpy(c).cuda()
+    lm = T.LogMelSpectrogram(**GEO).cuda()
+    y = lm(x, lengths=torch.tensor(lens, device="cuda", dtype=torch.int32), preemphasis=0.97)
+    for i, c in enumerate(clips):
+        Ti = 1 + len(c) // 256
+        ref = mo.log_mel_spectrogram(mo.pre_emphasis(c[None, None, :], 0.97)[:, 0], **GEO, clamp=False)[0]
+        assert mo.parity_error(y[i, :, :Ti].cpu().numpy(), ref) < TOL
+    buf = torch.zeros(5 * 22050 + 8, device="cuda")
+    v = buf[1:1 + 5 * 22050].view(5, 22050)
+    xs = cuda(torch, mo.synth_clips(5, 22050, 22050, seed=9))
+    v.copy_(xs)
+    assert torch.equal(lm(v, preemphasis=0.97), lm(xs, preemphasis=0.97))
