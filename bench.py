@@ -437,6 +437,7 @@ def main():
     #   nccl        kernel -> dist.all_gather_into_tensor (eager launches: NCCL does not replay from a graph here)
     #   fused_pull  kernel writes into the symmetric buffer -> b200mel_gather_pull: in-kernel barrier + 16-byte peer
     #               loads (SM kernel; the persistent extraction kernel fills the SMs, so the two serialise)
+    #   fused_pull_splitR  the extraction runs on 148 - R SMs, the pull (2 R CTAs) beside it on the other R
     #   fused_copy  same buffer -> one-CTA barrier kernel + copy-engine peer copies (overlaps with the extraction)
     # The fused pipelines are captured in ONE CUDA graph (8 steps, two streams) and replayed: no host launch cost in
     # the timed region, like the `value` leg.
@@ -481,12 +482,14 @@ def main():
                                     "second stream, eager launches"}
         a0 = rank * B_PER_GPU
         ingress = (world - 1) * B_PER_GPU * N_MELS * T * 4
-        for engine in ("pull", "copy"):
-            key = "fused_" + engine
+        variants = [("fused_pull", "pull", 0), ("fused_copy", "copy", 1)]
+        variants += [(f"fused_pull_split{r}", "pull", r) for r in (24, 32, 48)]
+        for key, engine, spare in variants:
             try:
-                sg = SymmetricGather(engine=engine)
+                sg = SymmetricGather(engine=engine, pull_ctas=2 * spare if engine == "pull" else 0)
 
-                spare = 1 if engine == "copy" else 0  # one SM for the barrier CTA that gates the copy-engine transfers
+                # spare = SMs the extraction leaves free: 1 for the barrier CTA that gates the copy engines, R for a
+                # pull kernel of 2 R CTAs running beside it, 0 when the pull uses the whole GPU after the extraction
 
                 def fused_launch(i, spare=spare, sg=sg):
                     full = sg.slot(world * B_PER_GPU, N_MELS, T, dev)
@@ -523,7 +526,9 @@ def main():
                                "nvlink_ingress_gbs_per_gpu": ingress / (ms_f * 1e-3) / 1e9,
                                "nvlink_frac_of_770": ingress / (ms_f * 1e-3) / 1e9 / 770.0,
                                "method": ("extraction kernel writes its block into a torch symmetric-memory buffer; "
-                                          + ("b200mel_gather_pull: in-kernel barrier + 16-byte peer loads (SM kernel)"
+                                          + ((f"b200mel_gather_pull: in-kernel barrier + 16-byte peer loads, SM kernel on "
+                                              + (f"{spare} SMs beside the extraction on the other {148 - spare}" if spare
+                                                 else "all SMs after the extraction"))
                                              if engine == "pull" else
                                              "b200mel_gather_copy: one-CTA barrier kernel + copy-engine peer copies")
                                           + f"; gather of step i on a second stream under the extraction of step i+1; "

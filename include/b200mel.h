@@ -236,8 +236,14 @@ int b200mel_mel_to_mfcc(const float *mel, const float *dct, int64_t B, int32_t n
  * overwrite its block while peers may still be pulling it: rotate three buffers and order the extraction of step i
  * after this rank's gather of step i-2 (pytorch_sound_b200/distributed.py). */
 int b200mel_gather_pull(float *local_buf, const float *const *peer_bufs, int32_t *const *peer_sync, int32_t world,
-                        int32_t rank, const int64_t *block_offsets /* [world + 1] */, void *stream);
-/* Same gather with the COPY ENGINES doing the transfers: a one-CTA barrier kernel (peer_sync is required), then one
+                        int32_t rank, const int64_t *block_offsets /* [world + 1] */,
+                        int32_t n_ctas /* 512-thread CTAs of the pull kernel; 0 = two per SM */, void *stream);
+/* SM partitioning: the extraction kernel is persistent and owns every register of the SMs it runs on, so a pull
+ * kernel launched on another stream only runs beside it on SMs the extraction left free — launch the extraction
+ * with b200mel_io.reserve_sms = R and the pull with n_ctas = 2 R and the two overlap (R ~ 32 of 148 SMs keeps
+ * NVLink busy while the extraction runs on the rest).
+ *
+ * Same gather with the COPY ENGINES doing the transfers: a one-CTA barrier kernel (peer_sync is required), then one
  * device-to-device copy per peer on internal streams forked from and joined back into `stream`.  The extraction
  * kernel is persistent and fills every SM, so an SM-resident pull cannot run beside it; the copy engines can — use
  * this variant when the gather of step i is overlapped with the extraction of step i+1 on another stream, and

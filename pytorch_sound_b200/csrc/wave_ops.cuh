@@ -144,7 +144,7 @@ struct PullArgs {
 // 0 publishes "my block of this step is written" (the extraction kernel precedes this launch in stream order) to
 // every peer with a system-scope release store; every CTA then spins (bounded, then traps) with system-scope
 // acquire loads on its OWN rank's flags until all peers have published this step.
-__global__ void __launch_bounds__(512) gather_pull_kernel(float *__restrict__ local, const PullArgs a) {
+__global__ void __launch_bounds__(512, 2) gather_pull_kernel(float *__restrict__ local, const PullArgs a) {
     int *sync = a.peer_sync[a.rank];
     __shared__ int s_step;
     if (sync) {
@@ -165,36 +165,55 @@ __global__ void __launch_bounds__(512) gather_pull_kernel(float *__restrict__ lo
     }
     const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long nthreads = (long long)gridDim.x * blockDim.x;
-    for (int i = 1; i < (a.pull ? a.world : 1); ++i) {
-        const int r = (a.rank + i) % a.world;  // stagger the peers: at any moment the ranks read from different GPUs
-        const long long lo = a.off[r], hi = a.off[r + 1];
-        const float *src = a.peer[r];
-        // head / tail to 16-byte alignment with scalar loads, body with 4 x 16-byte loads in flight per thread
-        const long long body_lo = (lo + 3) & ~3LL, body_hi = hi & ~3LL;
-        if (body_lo >= body_hi) {
-            for (long long e = lo + tid; e < hi; e += nthreads) local[e] = *reinterpret_cast<const volatile float *>(src + e);
-            continue;
+    if (a.pull) {
+        // Peer-interleaved: one 16-byte load per peer in flight per thread (groups of 8 peers), so every link is busy for
+        // the whole kernel and nothing drains between peers.  Block heads / tails that are not 16-byte aligned go
+        // through scalar loads.  Pointers and offsets are re-derived from the kernel parameters (constant bank) at every
+        // use: the kernel must stay at <= 64 registers so that two 512-thread CTAs fit on an SM.
+        auto body = [&](int r, long long &lo4, long long &n4) {  // 16-byte aligned body of block r, in floats / float4s
+            const long long lo = a.off[r], hi = a.off[r + 1];
+            long long b_lo = (lo + 3) & ~3LL, b_hi = hi & ~3LL;
+            if (b_lo >= b_hi) b_lo = b_hi = hi;
+            lo4 = b_lo;
+            n4 = (b_hi - b_lo) >> 2;
+        };
+        long long n4_max = 0;
+        for (int r = 0; r < a.world; ++r) {
+            if (r == a.rank) continue;
+            const long long lo = a.off[r], hi = a.off[r + 1];
+            long long lo4, n4;
+            body(r, lo4, n4);
+            const float *src = a.peer[r];
+            for (long long e = lo + tid; e < min(lo4, hi); e += nthreads) local[e] = *reinterpret_cast<const volatile float *>(src + e);
+            for (long long e = lo4 + 4 * n4 + tid; e < hi; e += nthreads) local[e] = *reinterpret_cast<const volatile float *>(src + e);
+            n4_max = max(n4_max, n4);
         }
-        for (long long e = lo + tid; e < body_lo; e += nthreads) local[e] = *reinterpret_cast<const volatile float *>(src + e);
-        for (long long e = body_hi + tid; e < hi; e += nthreads) local[e] = *reinterpret_cast<const volatile float *>(src + e);
-        const long long n4 = (body_hi - body_lo) >> 2;
-        const float4 *s4 = reinterpret_cast<const float4 *>(src + body_lo);
-        float4 *d4 = reinterpret_cast<float4 *>(local + body_lo);
-        long long k = tid;
-        for (; k + 3 * nthreads < n4; k += 4 * nthreads) {
-            float4 v[4];
+#pragma unroll 1
+        for (int g = 0; g < a.world; g += 8) {
+            for (long long k = tid; k < n4_max; k += nthreads) {
+                float4 v[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
-                             : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
-                             : "l"(s4 + k + u * nthreads));
+                for (int i = 0; i < 8; ++i) {
+                    const int r = g + i;
+                    if (r < a.world && r != a.rank) {
+                        long long lo4, n4;
+                        body(r, lo4, n4);
+                        if (k < n4)
+                            asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
+                                         : "l"(reinterpret_cast<const float4 *>(a.peer[r] + lo4) + k));
+                    }
+                }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) d4[k + u * nthreads] = v[u];
-        }
-        for (; k < n4; k += nthreads) {
-            float4 v;
-            asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(s4 + k));
-            d4[k] = v;
+                for (int i = 0; i < 8; ++i) {
+                    const int r = g + i;
+                    if (r < a.world && r != a.rank) {
+                        long long lo4, n4;
+                        body(r, lo4, n4);
+                        if (k < n4) reinterpret_cast<float4 *>(local + lo4)[k] = v[i];
+                    }
+                }
+            }
         }
     }
     if (sync) {  // the last CTA of the launch advances the epoch

@@ -74,8 +74,9 @@ class SymmetricGather:
 
     N_SLOTS = 3
 
-    def __init__(self, group=None, engine: str = "pull"):
-        """engine="pull": SM kernel with 16-byte peer loads (fastest when the gather runs alone);
+    def __init__(self, group=None, engine: str = "pull", pull_ctas: int = 0):
+        """engine="pull": SM kernel with 16-byte peer loads (fastest; to overlap it with an extraction on another stream,
+        launch that extraction with reserve_sms=R and give the pull pull_ctas=2 R);
         engine="copy": one-CTA barrier kernel + copy-engine transfers (overlaps with an extraction kernel that fills
         the SMs on another stream)."""
         import torch.distributed._symmetric_memory as symm_mem
@@ -83,6 +84,7 @@ class SymmetricGather:
         if engine not in ("pull", "copy"):
             raise ValueError("engine must be 'pull' or 'copy'")
         self.engine = engine
+        self.pull_ctas = int(pull_ctas)  # CTAs of the pull kernel (0 = two per SM); 2 R beside an extraction with reserve_sms=R
 
         self._symm = symm_mem
         self.group = group if group is not None else dist.group.WORLD
@@ -139,9 +141,12 @@ class SymmetricGather:
                     (C.c_int64 * (self.world + 1))(*offs))
             self._call_args[key] = args
         with torch.cuda.device(buf.device):
-            fn = _lib.lib().b200mel_gather_pull if self.engine == "pull" else _lib.lib().b200mel_gather_copy
-            rc = fn(buf.data_ptr(), args[0], args[1], self.world, self.rank, args[2],
-                    C.c_void_p(torch.cuda.current_stream(buf.device).cuda_stream))
+            st = C.c_void_p(torch.cuda.current_stream(buf.device).cuda_stream)
+            if self.engine == "pull":
+                rc = _lib.lib().b200mel_gather_pull(buf.data_ptr(), args[0], args[1], self.world, self.rank, args[2],
+                                                    self.pull_ctas, st)
+            else:
+                rc = _lib.lib().b200mel_gather_copy(buf.data_ptr(), args[0], args[1], self.world, self.rank, args[2], st)
         _lib.check(rc)
         return buf[:n_clips * per_clip].view(n_clips, n_mels, n_frames)
 
