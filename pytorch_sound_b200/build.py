@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libb200mel.so")
 SOURCES = ["b200mel.cu"]
-HEADERS = ["fft32.cuh", "logmel_kernel.cuh", "spec_kernel.cuh", "wave_ops.cuh", os.path.join("..", "..", "include", "b200mel.h")]
+HEADERS = ["fft32.cuh", "logmel_kernel.cuh", "logmel_fast.cuh", "mel_tc.cuh", "stft_tc.cuh", "stft_tc_tables.h", "spec_kernel.cuh", "wave_ops.cuh", os.path.join("..", "..", "include", "b200mel.h")]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",

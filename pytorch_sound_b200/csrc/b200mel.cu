@@ -28,6 +28,9 @@
 #include "logmel_fast.cuh"
 #include "mel_tc.cuh"
 #include "spec_kernel.cuh"
+#include "stft_tc.cuh"
+#include "stft_tc_tables.h"
+#include "stc_probe.cuh"
 #include "wave_ops.cuh"
 
 namespace b200mel {
@@ -42,6 +45,9 @@ static const bool g_pdl = [] {  // B200MEL_PDL=0 disables programmatic dependent
     return !(e && e[0] == '0');
 }();
 static const bool g_table_window = getenv("B200MEL_TABLE_WINDOW") != nullptr;  // A/B: read the Hann table instead
+#ifndef B200MEL_TC_DEFAULT
+#define B200MEL_TC_DEFAULT 0  // 2: auto (eligible plans, launches that fill the GPU); 0: only when B200MEL_TC is set
+#endif
 static long long *g_dbg = nullptr;  // device buffer for -DB200MEL_PHASE_TIMING builds (b200mel_debug_set_buffer)
 
 static int fail(int code, const std::string &msg) {
@@ -129,6 +135,10 @@ struct b200mel_plan {
     uint16_t *d_tc_bhi = nullptr, *d_tc_blo = nullptr;
     int tc_k_steps = 0, tc_n_pad = 0, tc_b_bytes = 0, tc_smem = 0;
     std::mutex tc_mu;
+    // tcgen05 STFT kernel (stft_tc.cuh): constant operands + mel schedule blob; null when the plan is not eligible
+    // (n_fft = win_length = 1024, hop 256, filterbank below bin 384, <= 128 mel rows)
+    unsigned char *d_stc = nullptr;
+    int stc_mel_bytes = 0, stc_smem = 0;
     // shared-memory layout
     int off_window = 0, off_entries = 0, off_melw = 0, off_bar = 0, off_regions = 0, region_bytes = 0, stage_bytes = 0;
     int n_warps = 0, smem_bytes = 0;
@@ -335,6 +345,33 @@ static int build_mel_schedule(bool pair, const float *W, int n_mels, int F, MelS
     return B200MEL_OK;
 }
 
+// Tensor-core STFT kernel: (re)build its operand blob for the plan's current filterbank.  Not an error when the plan
+// is outside the kernel's geometry — the plan then simply keeps using the CUDA-core kernels.
+static int stc_prepare(b200mel_plan *pl) {
+    cudaFree(pl->d_stc);
+    pl->d_stc = nullptr;
+    pl->stc_mel_bytes = pl->stc_smem = 0;
+    if (pl->cfg.n_fft != kStcNfft || pl->cfg.win_length != kStcNfft || pl->cfg.hop_length != kStcHop || pl->W_dense.empty())
+        return B200MEL_OK;
+    StcTables tb;
+    const char *why = nullptr;
+    if (!stc_build_tables(pl->W_dense.data(), pl->cfg.n_mels > 0 ? (int)(pl->W_dense.size() / pl->n_freq) : 0, pl->n_freq, &tb, &why))
+        return B200MEL_OK;
+    const int smem = kStcOffMel + tb.mel_bytes;
+    if (smem > kMaxSmem) return B200MEL_OK;
+    cudaError_t e;
+    if ((e = cudaMalloc(&pl->d_stc, tb.blob.size())) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = cudaMemcpy(pl->d_stc, tb.blob.data(), tb.blob.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return cuda_fail(e, "cudaMemcpy(tensor-core tables)");
+    for (int power = 1; power <= 2; ++power) {
+        e = cudaFuncSetAttribute(power == 2 ? stft_tc_kernel<2> : stft_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stft_tc_kernel)");
+    }
+    pl->stc_mel_bytes = tb.mel_bytes;
+    pl->stc_smem = smem;
+    return B200MEL_OK;
+}
+
 static int upload_filterbank(b200mel_plan *pl, const float *W_log, int n_mels, int F_log) {
     MelSchedule sch;
     pl->W_dense.assign(W_log, W_log + (size_t)n_mels * F_log);
@@ -364,7 +401,8 @@ static int upload_filterbank(b200mel_plan *pl, const float *W_log, int n_mels, i
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(filterbank)");
     pl->mel_rounds = sch.rounds;
     pl->mel_w_len = (int)sch.w.size();
-    return layout_smem(pl);
+    if (int rc = layout_smem(pl)) return rc;
+    return stc_prepare(pl);
 }
 
 typedef void (*kernel_fn)(const KParams);
@@ -423,7 +461,60 @@ static kernel_fn pick_fast_kernel(const b200mel_plan *pl) {
     return nullptr;
 }
 
+// The tensor-core STFT kernel is used for every eligible plan and launch unless B200MEL_TC=0; B200MEL_TC=1 also uses
+// it for launches too small to fill the GPU (fewer 8-frame batches than half the SMs), which the per-warp kernel serves better.
+static std::atomic<int> g_stc_mode{[] {
+    const char *e = getenv("B200MEL_TC");
+    return e ? atoi(e) : B200MEL_TC_DEFAULT;
+}()};
+static void *g_stc_taps[4] = {nullptr, nullptr, nullptr, nullptr};
+static std::atomic<long long> g_stc_launches{0};
+static bool stc_enabled(const b200mel_plan *pl, int64_t T, int64_t B) {
+    const int mode = g_stc_mode.load();
+    if (!pl->d_stc || mode == 0) return false;
+    if (mode == 1) return true;
+    return ((T + kStcGroup - 1) / kStcGroup) * B >= pl->num_sms / 2;
+}
+
 extern "C" {
+
+// debug hooks, not part of include/b200mel.h.  Taps of the tensor-core STFT kernel for the NEXT launches (device
+// pointers, null = off): [0] magnitudes (B, 384, T), [1] summed stage-1 accumulators of batch 0 [(n2, t)][32],
+// [2] summed stage-2 accumulators of batch 0 [(slot, t)][48], [3] unused.
+void b200mel_debug_set_tc_taps(void *mag, void *d1, void *d2, void *a2) {
+    g_stc_taps[0] = mag, g_stc_taps[1] = d1, g_stc_taps[2] = d2, g_stc_taps[3] = a2;
+}
+int64_t b200mel_debug_tc_launch_count(void) { return g_stc_launches.load(); }
+// 0: never, 1: every eligible launch, 2: eligible launches that fill the GPU; returns the previous mode
+int b200mel_debug_set_tc_mode(int mode) { return g_stc_mode.exchange(mode); }
+// host only, no GPU: the operand blob stft_tc_kernel would use for a dense (n_mels, 513) filterbank.  Returns the
+// number of bytes written (<= cap), -1 if the filterbank is not eligible.  info[0] = mel bytes, [1] = row groups,
+// [2] = longest group, [3] = cost of the busiest warp.
+int64_t b200mel_debug_tc_tables(const float *W, int32_t n_mels, int32_t n_freq, unsigned char *out, int64_t cap, int32_t *info) {
+    StcTables tb;
+    const char *why = nullptr;
+    if (!W || !stc_build_tables(W, n_mels, n_freq, &tb, &why)) return -1;
+    if (info) info[0] = tb.mel_bytes, info[1] = tb.n_groups, info[2] = tb.max_len, info[3] = tb.warp_cost_max;
+    if (out && cap >= (int64_t)tb.blob.size()) memcpy(out, tb.blob.data(), tb.blob.size());
+    return (int64_t)tb.blob.size();
+}
+
+// debug hook (tools/tc_bench.py probe): times chains of tcgen05.mma for n_cfg operand layouts, 8 uint32 per config
+// {a_off, a_lbo, a_sbo, b_off, b_lbo, b_sbo, n, chain}; out = 2 int64 per config {issue cycles, issue + completion cycles}
+int b200mel_debug_mma_probe(const uint32_t *cfgs, int32_t n_cfg, long long *out_host) {
+    ProbeCfg *d_cfg = nullptr;
+    long long *d_out = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_cfg, n_cfg * sizeof(ProbeCfg))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&d_out, n_cfg * 16)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    cudaMemcpy(d_cfg, cfgs, n_cfg * sizeof(ProbeCfg), cudaMemcpyHostToDevice);
+    cudaFuncSetAttribute(stc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    stc_probe_kernel<<<1, 128, 200 * 1024>>>(d_cfg, n_cfg, d_out);
+    e = cudaMemcpy(out_host, d_out, n_cfg * 16, cudaMemcpyDeviceToHost);
+    cudaFree(d_cfg);
+    cudaFree(d_out);
+    return e == cudaSuccess ? B200MEL_OK : cuda_fail(e, "mma probe");
+}
 
 int b200mel_version(void) { return B200MEL_VERSION; }
 const char *b200mel_last_error(void) { return g_err.c_str(); }
@@ -605,6 +696,7 @@ int b200mel_plan_destroy(b200mel_plan *pl) {
     free_mel_tables(pl);
     cudaFree(pl->d_tc_bhi);
     cudaFree(pl->d_tc_blo);
+    cudaFree(pl->d_stc);
     for (auto &hs : pl->host_stage) {
         cudaFree(hs.d_in);
         cudaFree(hs.d_out);
@@ -755,7 +847,27 @@ int b200mel_forward_io(const b200mel_plan *pl, const b200mel_io *io, const b200m
     cfg.numAttrs = 1;
     cudaError_t le = cudaSuccess;
     // mel and spectrum outputs come from separately specialised kernels (no reference module needs both at once)
-    if (out_mel) {
+    if (out_mel && stc_enabled(pl, T, B) && !lengths && !p.out_fmask && p.preemph == 0.f && !spec_kind) {
+        // both DFT stages on the tensor cores (stft_tc.cuh)
+        StcParams sp;
+        memset(&sp, 0, sizeof(sp));
+        sp.k = p;
+        sp.tables = pl->d_stc;
+        sp.mel_bytes = pl->stc_mel_bytes;
+        sp.groups_per_clip = (int)((T + kStcGroup - 1) / kStcGroup);
+        sp.n_batches = (long long)sp.groups_per_clip * B;
+        sp.power = pl->cfg.power;
+        sp.dbg_mag = g_stc_taps[0] ? (float *)g_stc_taps[0] : nullptr;
+        sp.dbg_d1 = (float *)g_stc_taps[1];
+        sp.dbg_d2 = (float *)g_stc_taps[2];
+        sp.dbg_a2 = (unsigned char *)g_stc_taps[3];
+        cfg.gridDim = dim3((unsigned)std::min<long long>(sp.n_batches, usable_sms));
+        cfg.blockDim = dim3(kStcThreads);
+        cfg.dynamicSmemBytes = pl->stc_smem;
+        le = pl->cfg.power == 2 ? cudaLaunchKernelEx(&cfg, stft_tc_kernel<2>, sp) : cudaLaunchKernelEx(&cfg, stft_tc_kernel<1>, sp);
+        g_launches.fetch_add(1);
+        g_stc_launches.fetch_add(1);
+    } else if (out_mel) {
         cfg.gridDim = dim3((unsigned)n_cta);
         cfg.blockDim = dim3(pl->n_warps * 32);
         kernel_fn fn = (!lengths && p.use_log && !p.out_fmask && p.preemph == 0.f) ? pick_fast_kernel(pl) : nullptr;
