@@ -364,7 +364,7 @@ static int stc_prepare(b200mel_plan *pl) {
     if ((e = cudaMemcpy(pl->d_stc, tb.blob.data(), tb.blob.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
         return cuda_fail(e, "cudaMemcpy(tensor-core tables)");
     for (int power = 1; power <= 2; ++power) {
-        e = cudaFuncSetAttribute(power == 2 ? stft_tc_kernel<2> : stft_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        e = cudaFuncSetAttribute(power == 2 ? stft_tc_kernel<2> : stft_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stft_tc_kernel)");
     }
     pl->stc_mel_bytes = tb.mel_bytes;
@@ -472,8 +472,10 @@ static std::atomic<long long> g_stc_launches{0};
 static bool stc_enabled(const b200mel_plan *pl, int64_t T, int64_t B) {
     const int mode = g_stc_mode.load();
     if (!pl->d_stc || mode == 0) return false;
+    const int64_t batches = ((T + kStcGroup - 1) / kStcGroup) * B;
+    if (batches > 0x7fffffff) return false;   // the kernel walks its batches with 32-bit arithmetic
     if (mode == 1) return true;
-    return ((T + kStcGroup - 1) / kStcGroup) * B >= pl->num_sms / 2;
+    return batches >= pl->num_sms / 2;
 }
 
 extern "C" {

@@ -44,7 +44,9 @@
 
 namespace b200mel {
 
-constexpr int kStcThreads = 512;
+constexpr int kStcTwWarps = 8, kStcSpecWarps = 4, kStcEdgeWarps = 4, kStcMelWarps = 4;
+constexpr int kStcWorkWarps = kStcTwWarps + kStcSpecWarps + kStcEdgeWarps + kStcMelWarps;   // 20
+constexpr int kStcThreads = (kStcWorkWarps + 1) * 32;                        // + the issuer warp
 constexpr int kStcGroup = 8;                         // frames per batch
 constexpr int kStcHop = 256, kStcNfft = 1024;
 constexpr int kStcSpan = (kStcGroup - 1) * kStcHop + kStcNfft;  // 2816 samples per batch
@@ -53,28 +55,45 @@ constexpr int kStcPitch = kStcQ * 2;                 // 176 bytes = 11 x 16: odd
 constexpr int kStcBins = 384;                        // spectrum bins produced
 constexpr int kStcMagPad = 4;                        // zero rows in front of the magnitude tile (mel windows may start at -3)
 constexpr int kStcShift = 6;                         // stage-2 operands are scaled by 2^-6
-constexpr int kStcMaxGroups = 32;                    // mel rows / 4
-constexpr int kStcMelSlots = 4;                      // row groups a warp may own
+constexpr int kStcMaxMels = kStcMelWarps * 32;       // one mel row per thread of the mel warps
+constexpr int kStcOutPitch = 12;                     // floats per row of a mel warp's transpose tile (8 used)
 
-// shared-memory carve-up (bytes)
+// shared-memory carve-up (bytes); S, A2 and the magnitude tile are double-buffered
 constexpr int kStcStageBytes = 11392;                // (2816 + 8) floats rounded to 128
 constexpr int kStcOffStage = 0;
-constexpr int kStcOffHank = 2 * kStcStageBytes;                  // hi limb, then lo limb
+constexpr int kStcOffHank = 2 * kStcStageBytes;                  // per buffer: hi limb, then lo limb
 constexpr int kStcHankBytes = 32 * kStcPitch;                    // 5632
-constexpr int kStcOffB1 = kStcOffHank + 2 * kStcHankBytes;       // [4 k chunks][64 n][8 k] fp16
+constexpr int kStcOffB1 = kStcOffHank + 4 * kStcHankBytes;       // [4 k chunks][64 n][8 k] fp16
 constexpr int kStcB1Bytes = 4096;
-constexpr int kStcOffA2 = kStcOffB1 + kStcB1Bytes;               // hi tile, then lo tile: [8 k chunks][16 slots][8 frames][8 k]
+constexpr int kStcOffA2 = kStcOffB1 + kStcB1Bytes;               // per buffer: hi tile, lo tile: [8 k chunks][16 slots][8 frames][8 k]
 constexpr int kStcA2Bytes = 16384;
-constexpr int kStcOffB2 = kStcOffA2 + 2 * kStcA2Bytes;           // [8 k chunks][192 n][8 k] fp16
+constexpr int kStcOffB2 = kStcOffA2 + 4 * kStcA2Bytes;           // [8 k chunks][192 n][8 k] fp16
 constexpr int kStcB2Bytes = 24576;
 constexpr int kStcOffTw = kStcOffB2 + kStcB2Bytes;               // float2 [17][32]
 constexpr int kStcTwBytes = 17 * 32 * 8;
-constexpr int kStcOffMag = kStcOffTw + kStcTwBytes;              // float [4 + 384][8]
+constexpr int kStcOffMag = kStcOffTw + kStcTwBytes;              // 2 x float [4 + 384][8]
 constexpr int kStcMagBytes = (kStcMagPad + kStcBins) * kStcGroup * 4;
-constexpr int kStcOffMisc = kStcOffMag + kStcMagBytes;           // mbarriers, TMEM address, per-warp maxima, descale ring
-constexpr int kStcMiscBytes = 256;
-constexpr int kStcOffMel = kStcOffMisc + kStcMiscBytes;          // mel schedule (header + weights), size from the plan
-constexpr int kStcMelHeader = (16 * kStcMelSlots + 2 * kStcMaxGroups) * 4 + kStcMaxGroups * 4 * 8;  // grp | glen | gwoff | ent
+constexpr int kStcOffMisc = kStcOffMag + 2 * kStcMagBytes;       // mbarriers, TMEM address, per-warp maxima, descale ring
+constexpr int kStcMiscBytes = 384;
+constexpr int kStcOffOut = kStcOffMisc + kStcMiscBytes;          // per mel warp: float [32 rows][kStcOutPitch] transpose tile
+constexpr int kStcOutBytes = 32 * kStcOutPitch * 4;
+constexpr int kStcOffMel = kStcOffOut + kStcMelWarps * kStcOutBytes;  // mel schedule (header + weights), size from the plan
+constexpr int kStcMelHeader = 2 * kStcMelWarps * 4 + kStcMaxMels * 8;  // trip[4] | woff[4] | ent[128] {m, lo}
+
+// mbarriers (index into the array at kStcOffMisc)
+enum {
+    kBarStageFull = 0,    // [2] TMA landed                       -> edge warps
+    kBarStageEmpty = 2,   // [2] edge warps read the stage        -> issuer (next TMA into it)
+    kBarSFull = 4,        // [2] Hankel buffer written            -> issuer (M1)
+    kBarD1Full = 6,       // [2] M1 complete (commit)             -> twiddle warps; also: Hankel buffer free -> edge warps
+    kBarD1Empty = 8,      // [2] twiddle warps read D1            -> issuer (M1 two batches on)
+    kBarA2Full = 10,      // [2] stage-2 operand written          -> issuer (M2)
+    kBarD2Full = 12,      // [2] M2 complete (commit)             -> spectrum warps; also: A2 buffer free -> twiddle warps
+    kBarD2Empty = 14,     // [1] spectrum warps read D2           -> issuer (next M2)
+    kBarMagFull = 15,     // [2] magnitude tile written           -> mel warps
+    kBarMagEmpty = 17,    // [2] mel warps read the tile          -> spectrum warps (two batches on)
+    kStcNumBars = 19
+};
 
 struct StcParams {
     KParams k;                   // waveform geometry, outputs, epilogue (the fields copy_geom / epilogue() read)
@@ -122,28 +141,89 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void split_f16x2(float x, float y, uint32_t &hi, uint32_t &lo) {
     const __half2 h = __floats2half2_rn(x, y);
     const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+    const float2 d = __fadd2_rn(make_float2(x, y), make_float2(-hf.x, -hf.y));
+    const __half2 l = __floats2half2_rn(d.x, d.y);
     hi = *reinterpret_cast<const uint32_t *>(&h);
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0u;
+}
+// mbarrier wait that parks the warp in hardware (suspend-time hint, as CUTLASS' ClusterBarrier::wait does) instead of
+// spinning: the role warps of this kernel spend most of their time waiting for each other, and a spinning warp
+// competes for issue slots with the working warps of its scheduler (measured: 45 % of all executed instructions
+// were try_wait loops before this).
+__device__ __forceinline__ void mbar_park(uint32_t bar, uint32_t parity) {
+    uint32_t done, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(0x989680u)
+            : "memory");
+        if (!done && ++spins > (1u << 20)) __trap();
+    } while (!done);
+}
+// one arrival per warp: every lane's prior work is ordered before it by the __syncwarp
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+
+// Per-role cycle accounting (-DB200MEL_STC_TIMING, tools/tc_bench.py timing): lane 0 of one warp per role adds its
+// clock64() deltas to dbg[role * 8 + slot]; roles: 0 issuer, 1 twiddle, 2 spectrum, 3 edge.
+#ifdef B200MEL_STC_TIMING
+#define STC_TIMER() long long stc_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, stc_mark = clock64()
+#define STC_MARK(i)                        \
+    do {                                   \
+        const long long now_ = clock64();  \
+        stc_acc[i] += now_ - stc_mark;     \
+        stc_mark = now_;                   \
+    } while (0)
+#define STC_FLUSH(role)                                                                                        \
+    do {                                                                                                       \
+        if (lane == 0 && p.k.dbg)                                                                              \
+            for (int i_ = 0; i_ < 8; ++i_)                                                                     \
+                atomicAdd(reinterpret_cast<unsigned long long *>(p.k.dbg) + (role) * 8 + i_, (unsigned long long)stc_acc[i_]); \
+    } while (0)
+#else
+#define STC_TIMER() do { } while (0)
+#define STC_MARK(i) do { } while (0)
+#define STC_FLUSH(role) do { } while (0)
+#endif
 
 template <int kPower>
 __global__ void __launch_bounds__(kStcThreads, 1) stft_tc_kernel(const StcParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float *s_mag = reinterpret_cast<float *>(smem + kStcOffMag);
     const float2 *s_tw = reinterpret_cast<const float2 *>(smem + kStcOffTw);
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + kStcOffMisc);  // [0,1] TMA, [2] M1, [3,4] M2
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kStcOffMisc + 48);
-    uint32_t *s_wmax = reinterpret_cast<uint32_t *>(smem + kStcOffMisc + 64);  // [16]
-    float *s_descale = reinterpret_cast<float *>(smem + kStcOffMisc + 128);    // [4]
-    const int *s_grp = reinterpret_cast<const int *>(smem + kStcOffMel);                       // [16][kStcMelSlots]
-    const int *s_glen = s_grp + 16 * kStcMelSlots;                                              // [kStcMaxGroups]
-    const int *s_gwoff = s_glen + kStcMaxGroups;                                                // [kStcMaxGroups]
-    const int2 *s_ent = reinterpret_cast<const int2 *>(s_gwoff + kStcMaxGroups);                // [kStcMaxGroups * 4] {m, lo}
-    const float *s_melw = reinterpret_cast<const float *>(smem + kStcOffMel + kStcMelHeader);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + kStcOffMisc);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kStcOffMisc + 160);
+    uint32_t *s_wmax = reinterpret_cast<uint32_t *>(smem + kStcOffMisc + 176);  // [2][4]
+    float *s_descale = reinterpret_cast<float *>(smem + kStcOffMisc + 208);     // [8]
+    int *s_geo = reinterpret_cast<int *>(smem + kStcOffMisc + 256);             // [2][8] per stage buffer: what the issuer staged
+    const int *s_trip = reinterpret_cast<const int *>(smem + kStcOffMel);                        // [kStcMelWarps]
+    const int *s_woff = s_trip + kStcMelWarps;                                                    // [kStcMelWarps]
+    const int2 *s_ent = reinterpret_cast<const int2 *>(s_woff + kStcMelWarps);                    // [kStcMaxMels] {m, lo}
+    const float *s_melw = reinterpret_cast<const float *>(smem + kStcOffMel + kStcMelHeader);     // per warp [trip][32 lanes]
+    const uint32_t sm_base = smem_u32(smem);
+    auto bar = [&](int i) { return smem_u32(s_bar + i); };
 
-    // ------------------------------------------------------------------ one-time setup
+    // ------------------------------------------------------------------ one-time setup (all 17 warps)
     {   // constant operands and schedules: one contiguous blob per destination
         const int4 *src = reinterpret_cast<const int4 *>(p.tables);
         int4 *d1 = reinterpret_cast<int4 *>(smem + kStcOffB1);
@@ -157,13 +237,18 @@ __global__ void __launch_bounds__(kStcThreads, 1) stft_tc_kernel(const StcParams
         src += kStcTwBytes / 16;
         int4 *d4 = reinterpret_cast<int4 *>(smem + kStcOffMel);
         for (int i = tid; i < p.mel_bytes / 16; i += kStcThreads) d4[i] = __ldg(src + i);
-        for (int i = tid; i < kStcMagPad * kStcGroup; i += kStcThreads) s_mag[i] = 0.f;
+        float *mg = reinterpret_cast<float *>(smem + kStcOffMag);
+        for (int i = tid; i < kStcMagPad * kStcGroup; i += kStcThreads) mg[i] = 0.f, mg[kStcMagBytes / 4 + i] = 0.f;
     }
     if (tid == 0) {
-        for (int i = 0; i < 5; ++i) mbar_init(smem_u32(s_bar + i), 1);
+        static_assert(kStcNumBars * 8 <= 160, "mbarriers overlap the scalars behind them");
+        const int counts[kStcNumBars] = {1, 1, kStcEdgeWarps, kStcEdgeWarps, kStcEdgeWarps, kStcEdgeWarps, 1, 1, kStcTwWarps, kStcTwWarps,
+                                         kStcTwWarps, kStcTwWarps, 1, 1, kStcSpecWarps, kStcSpecWarps, kStcSpecWarps, kStcMelWarps, kStcMelWarps};
+        static_assert(kBarMagEmpty + 2 == kStcNumBars, "barrier table out of date");
+        for (int i = 0; i < kStcNumBars; ++i) mbar_init(bar(i), counts[i]);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (warp == kStcWorkWarps) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -172,326 +257,377 @@ __global__ void __launch_bounds__(kStcThreads, 1) stft_tc_kernel(const StcParams
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
-    const uint32_t tm_d1 = tmem;            // 2 tiles x 64 columns
-    const uint32_t tm_d2 = tmem + 128;      // 2 buffers x 192 columns
+    const uint32_t tm_d1 = tmem;            // 2 buffers x (2 tiles x 64 columns)
+    const uint32_t tm_d2 = tmem + 256;      // 192 columns
 
     // instruction descriptors: D fp32, A / B fp16, both K-major, M = 128
     constexpr uint32_t kIdesc = (1u << 4) | (8u << 24);
     constexpr uint32_t kI64 = kIdesc | (8u << 17), kI32 = kIdesc | (4u << 17), kI192 = kIdesc | (24u << 17), kI96 = kIdesc | (12u << 17);
-    const uint32_t sm_base = smem_u32(smem);
 
-    const long long nb_total = p.n_batches;
-    const long long first = blockIdx.x, stride = gridDim.x;
+    const unsigned nb_total = (unsigned)p.n_batches;   // < 2^31 (checked by the host)
+    const unsigned first = blockIdx.x, stride = gridDim.x;
     const int n_mine = first < nb_total ? (int)((nb_total - first + stride - 1) / stride) : 0;
-    const int Gc = p.groups_per_clip;
+    const unsigned Gc = (unsigned)p.groups_per_clip;
 
     asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: nothing above touched caller memory
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    // geometry of my batch number i
-    auto batch_geom = [&](int i, long long &b, int &t0, int &s_first) {
-        const long long g = first + (long long)i * stride;
+    // geometry of my batch number j
+    auto batch_geom = [&](int j, unsigned &b, int &t0, int &s_first) {
+        const unsigned g = first + (unsigned)j * stride;
         b = g / Gc;
         t0 = (int)(g - b * Gc) * kStcGroup;
         s_first = t0 * kStcHop - p.k.pad;
     };
-    auto issue_tma = [&](int i) {  // one thread
-        long long b; int t0, s_first;
-        batch_geom(i, b, t0, s_first);
-        const CopyGeom g = copy_geom(p.k, b, s_first, kStcSpan, p.k.L);
-        issue_copy(g, sm_base + kStcOffStage + (i & 1) * kStcStageBytes, smem_u32(s_bar + (i & 1)));
-    };
 
-    // ---- P1: staged fp32 samples of batch i -> scaled fp16 limbs in the Hankel layout
-    auto phase1 = [&](int i) {
-        long long b; int t0, s_first;
-        batch_geom(i, b, t0, s_first);
-        float v[8];
-        uint32_t amax = 0u;
-        if (warp < 11) {
-            const CopyGeom g = copy_geom(p.k, b, s_first, kStcSpan, p.k.L);
-            mbar_wait(smem_u32(s_bar + (i & 1)), (uint32_t)(i >> 1) & 1u);
-            const float *st = reinterpret_cast<const float *>(smem + kStcOffStage + (i & 1) * kStcStageBytes) + g.delta - s_first;
-            const int s0 = s_first + 256 * warp + lane;  // q = 8 warp + j
-            if (!g.patch) {
+    if (warp == kStcWorkWarps) {
+        // ================================================================== issuer: TMA + tcgen05.mma, one thread
+        if (lane == 0 && n_mine > 0) {
+            int j_tma = 0, j_m1 = 0, j_m2 = 0;
+            uint32_t idle = 0;
+            STC_TIMER();
+            while (j_m2 < n_mine) {
+                bool progress = false;
+                STC_MARK(0);
+                if (j_tma < n_mine && (j_tma < 2 || mbar_test(bar(kBarStageEmpty + (j_tma & 1)), (uint32_t)((j_tma >> 1) - 1) & 1u))) {
+                    unsigned b; int t0, s_first;
+                    batch_geom(j_tma, b, t0, s_first);
+                    const CopyGeom g = copy_geom(p.k, (long long)b, s_first, kStcSpan, p.k.L);
+                    int *geo = s_geo + (j_tma & 1) * 8;   // read by the edge warps once the copy has landed
+                    geo[0] = (int)b, geo[1] = s_first, geo[2] = g.delta, geo[3] = g.c_lo, geo[4] = g.c_hi, geo[5] = g.patch ? 1 : 0;
+                    issue_copy(g, sm_base + kStcOffStage + (j_tma & 1) * kStcStageBytes, bar(kBarStageFull + (j_tma & 1)));
+                    ++j_tma;
+                    progress = true;
+                    STC_MARK(1);
+                }
+                // the older batch first: M2(j) before M1(j + 2)
+                if (j_m2 < j_m1 && mbar_test(bar(kBarA2Full + (j_m2 & 1)), (uint32_t)(j_m2 >> 1) & 1u) &&
+                    (j_m2 == 0 || mbar_test(bar(kBarD2Empty), (uint32_t)(j_m2 - 1) & 1u))) {
+                    tc_fence_after();
+                    const uint32_t a2 = sm_base + kStcOffA2 + (uint32_t)(j_m2 & 1) * 2u * kStcA2Bytes;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = st[s0 + 32 * j];
-            } else {
-                const float *row = p.k.wav + b * p.k.row_stride;
+                    for (int s = 0; s < 4; ++s) {
+                        const uint64_t a_hi = tc_desc(a2 + 4096u * s, 2048u, 128u);
+                        const uint64_t a_lo = tc_desc(a2 + kStcA2Bytes + 4096u * s, 2048u, 128u);
+                        const uint64_t bd = tc_desc(sm_base + kStcOffB2 + 6144u * s, 3072u, 128u);
+                        tc_mma(tm_d2, a_hi, bd, kI192, s);
+                        tc_mma(tm_d2, a_lo, bd, kI96, 1u);
+                    }
+                    tc_commit(bar(kBarD2Full + (j_m2 & 1)));
+                    ++j_m2;
+                    progress = true;
+                    STC_MARK(2);
+                }
+                if (j_m1 < n_mine && mbar_test(bar(kBarSFull + (j_m1 & 1)), (uint32_t)(j_m1 >> 1) & 1u) &&
+                    (j_m1 < 2 || mbar_test(bar(kBarD1Empty + (j_m1 & 1)), (uint32_t)((j_m1 >> 1) - 1) & 1u))) {
+                    tc_fence_after();
+                    const uint32_t hk = sm_base + kStcOffHank + (uint32_t)(j_m1 & 1) * 2u * kStcHankBytes;
+                    const uint32_t d1 = tm_d1 + 128u * (uint32_t)(j_m1 & 1);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int s = s0 + 32 * j;
-                    v[j] = (s >= g.c_lo && s < g.c_hi) ? st[s] : __ldg(row + reflect_index(s, p.k.L));
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int s = 0; s < 2; ++s) {
+                            const uint32_t a_off = (uint32_t)(16 * h * kStcPitch + 32 * s);
+                            const uint64_t a_hi = tc_desc(hk + a_off, 16u, (uint32_t)kStcPitch);
+                            const uint64_t a_lo = tc_desc(hk + kStcHankBytes + a_off, 16u, (uint32_t)kStcPitch);
+                            const uint64_t bd = tc_desc(sm_base + kStcOffB1 + 2048u * s, 1024u, 128u);
+                            tc_mma(d1 + 64u * h, a_hi, bd, kI64, s);
+                            tc_mma(d1 + 64u * h, a_lo, bd, kI32, 1u);
+                        }
+                    tc_commit(bar(kBarD1Full + (j_m1 & 1)));
+                    ++j_m1;
+                    progress = true;
+                    STC_MARK(3);
+                }
+                if (progress) idle = 0;
+                else {
+                    __nanosleep(64);                      // nothing ready: stay out of the working warps' issue slots
+                    if (++idle > (1u << 24)) __trap();    // protocol bug: a CUDA error instead of a hung GPU
                 }
             }
-            float m = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) m = fmaxf(m, fabsf(v[j]));  // NaN samples are caught below (fabsf keeps them out of fmaxf)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) if (!(fabsf(v[j]) <= 3.0e38f)) m = __uint_as_float(0x7f800000u);
-            amax = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+            STC_FLUSH(0);
         }
-        if (lane == 0) s_wmax[warp] = amax;
-        __syncthreads();
-        uint32_t mx = 0u;
-#pragma unroll
-        for (int w = 0; w < 16; ++w) mx = max(mx, s_wmax[w]);
-        // power-of-two scale: max |x| * sc in [2^13, 2^14); 1 for silence / non-finite input
-        int sexp = 127;
-        if (mx != 0u && mx < 0x7f800000u) {
-            sexp = 267 - (int)(mx >> 23);
-            sexp = min(max(sexp, 1), 254);
-            if (p.k.mag_eps > 0.f) sexp = min(sexp, 127 + 40);
-        }
-        const float sc = __uint_as_float((uint32_t)sexp << 23);
-        if (tid == 0) s_descale[i & 3] = __uint_as_float((uint32_t)(260 - sexp) << 23);  // 2^6 / sc
-        if (warp < 11) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) split_f16x2(v[2 * j] * sc, v[2 * j + 1] * sc, hi[j], lo[j]);
-            unsigned char *dst = smem + kStcOffHank + lane * kStcPitch + warp * 16;
-            *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4 *>(dst + kStcHankBytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        fence_proxy_async();
-    };
-    auto issue_m1 = [&]() {  // one thread, after the barrier that follows P1
-        tc_fence_after();
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const uint32_t a_off = (uint32_t)(16 * h * kStcPitch + 32 * s);
-                const uint64_t a_hi = tc_desc(sm_base + kStcOffHank + a_off, 16u, (uint32_t)kStcPitch);
-                const uint64_t a_lo = tc_desc(sm_base + kStcOffHank + kStcHankBytes + a_off, 16u, (uint32_t)kStcPitch);
-                const uint64_t bd = tc_desc(sm_base + kStcOffB1 + 2048u * s, 1024u, 128u);
-                tc_mma(tm_d1 + 64u * h, a_hi, bd, kI64, s);
-                tc_mma(tm_d1 + 64u * h, a_lo, bd, kI32, 1u);
-            }
-        tc_commit(smem_u32(s_bar + 2));
-    };
-
-    // ---- P2: D1 -> twiddle, Hann 3-tap -> fp16 limbs of the stage-2 operand
-    auto phase2 = [&](int i) {
-        const int quad = warp & 3, h = (warp >> 2) & 1, kh = warp >> 3;
+    } else if (warp < kStcTwWarps) {
+        // ================================================================== twiddle warps: P2
+        // D1 -> registers, hi + lo halves, twiddle, Hann 3-tap over k1, fp16 limbs -> stage-2 operand
+        const int quad = warp & 3, h = warp >> 2;
         const int n2 = 16 * h + 4 * quad + (lane >> 3), t = lane & 7;
-        const uint32_t ta = tm_d1 + ((uint32_t)(32 * quad) << 16) + 64u * h;
-        float a[20], l[20];   // kh 0: columns 0..19 (A0, A16, A1..A9); kh 1: [0..15] = columns 16..31 (A8..A15), [16..19] = columns 0..3
-        if (kh == 0) {
-            tmem_ld16(ta, a), tmem_ld4(ta + 16, a + 16), tmem_ld16(ta + 32, l), tmem_ld4(ta + 48, l + 16);
-        } else {
-            tmem_ld16(ta + 16, a), tmem_ld4(ta, a + 16), tmem_ld16(ta + 48, l), tmem_ld4(ta + 32, l + 16);
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 20; ++c) a[c] += l[c];
-        if (p.dbg_d1 && first == 0 && i == 0) {
-            float *d = p.dbg_d1 + (n2 * 8 + t) * 32;
-#pragma unroll
-            for (int c = 0; c < 20; ++c) d[kh == 0 ? c : (c < 16 ? 16 + c : c - 16)] = a[c];
-        }
-        const float S = 1.0f / (float)(1 << kStcShift);
-        float2 ap[10];    // twiddled values A'[k]: kh 0: k = 0..9; kh 1: k = 8..16 in [0..8]
-        float2 out0;      // kh 1: the packed row
         const float2 *tw = s_tw + n2;
-        if (kh == 0) {
-            ap[0] = make_float2(a[0] * S, 0.f);
-#pragma unroll
-            for (int k = 1; k < 10; ++k) ap[k] = cmul(make_float2(a[2 * k], a[2 * k + 1]), tw[32 * k]);
-        } else {
-#pragma unroll
-            for (int k = 8; k < 16; ++k) ap[k - 8] = cmul(make_float2(a[2 * (k - 8)], a[2 * (k - 8) + 1]), tw[32 * k]);
-            const float2 w16 = tw[32 * 16], w1 = tw[32];
-            ap[8] = make_float2(a[17] * w16.x, a[17] * w16.y);                 // A'[16] = W^(16 n2) A[16], A[16] real
-            const float2 ap1 = cmul(make_float2(a[18], a[19]), w1);            // A'[1]
-            out0.x = 0.5f * S * a[16] - 0.5f * ap1.x;                          // Aw'[0] (real)
-            out0.y = 0.5f * S * a[17] - 0.5f * fmaf(w1.x, a[14], w1.y * a[15]);  // r16: Aw'[16] = W64^n2 r16
-        }
-        unsigned char *dst = smem + kStcOffA2 + t * 16 + (n2 >> 2) * 2048 + (n2 & 3) * 4;
-#pragma unroll
-        for (int o = 0; o < 8; ++o) {
-            // kh 0: slots 1..8 (= k1); kh 1: slots 9..15 and the packed slot 0
-            const int slot = kh == 0 ? o + 1 : (o < 7 ? o + 9 : 0);
-            float2 w;
-            if (kh == 1 && o == 7) w = out0;
-            else {
-                const int c = kh == 0 ? o + 1 : o + 1;   // index of A'[slot] inside ap[]
-                w.x = fmaf(-0.25f, ap[c - 1].x + ap[c + 1].x, 0.5f * ap[c].x);
-                w.y = fmaf(-0.25f, ap[c - 1].y + ap[c + 1].y, 0.5f * ap[c].y);
-            }
-            uint32_t hi, lo;
-            split_f16x2(w.x, w.y, hi, lo);
-            *reinterpret_cast<uint32_t *>(dst + slot * 128) = hi;
-            *reinterpret_cast<uint32_t *>(dst + kStcA2Bytes + slot * 128) = lo;
-        }
-        fence_proxy_async();
-        tc_fence_before();
-    };
-    auto issue_m2 = [&](int i) {
-        tc_fence_after();
-        const uint32_t d = tm_d2 + 192u * (uint32_t)(i & 1);
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const uint64_t a_hi = tc_desc(sm_base + kStcOffA2 + 4096u * s, 2048u, 128u);
-            const uint64_t a_lo = tc_desc(sm_base + kStcOffA2 + kStcA2Bytes + 4096u * s, 2048u, 128u);
-            const uint64_t bd = tc_desc(sm_base + kStcOffB2 + 6144u * s, 3072u, 128u);
-            tc_mma(d, a_hi, bd, kI192, s);
-            tc_mma(d, a_lo, bd, kI96, 1u);
-        }
-        tc_commit(smem_u32(s_bar + 3 + (i & 1)));
-    };
-
-    // ---- P3: D2 -> magnitudes [bin][frame]
-    auto phase3 = [&](int i) {
-        const int quad = warp & 3, jq = warp >> 2;
-        const int slot = 4 * quad + (lane >> 3), t = lane & 7;
-        const uint32_t ta = tm_d2 + 192u * (uint32_t)(i & 1) + ((uint32_t)(32 * quad) << 16) + 12u * jq;
-        float a[12], l[12];
-        tmem_ld8(ta, a), tmem_ld4(ta + 8, a + 8), tmem_ld8(ta + 96, l), tmem_ld4(ta + 104, l + 8);
-        if (quad == 0) {  // rows 0..7 are the packed rows: their results are in the B' columns
-            float a2[12], l2[12];
-            tmem_ld8(ta + 48, a2), tmem_ld4(ta + 56, a2 + 8), tmem_ld8(ta + 144, l2), tmem_ld4(ta + 152, l2 + 8);
-            tmem_ld_wait();
-            if (lane < 8) {
-#pragma unroll
-                for (int c = 0; c < 12; ++c) a[c] = a2[c], l[c] = l2[c];
-            }
-        } else {
-            tmem_ld_wait();
-        }
-#pragma unroll
-        for (int c = 0; c < 12; ++c) a[c] += l[c];
-        if (p.dbg_d2 && first == 0 && i == 0) {
-            float *d = p.dbg_d2 + (slot * 8 + t) * 48 + 12 * jq;
-#pragma unroll
-            for (int c = 0; c < 12; ++c) d[c] = a[c];
-        }
-        const float descale = s_descale[i & 3];
-        const float eps = p.k.mag_eps > 0.f ? (p.k.mag_eps / descale) / descale : 0.f;
-        const int off2 = slot ? 32 - slot : 16;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            const int j = 6 * jq + c;
-            const int bin = jq < 2 ? slot + 32 * j : off2 + 32 * (23 - j);
-            s_mag[(kStcMagPad + bin) * kStcGroup + t] = magnitude<kPower>(a[2 * c], a[2 * c + 1], eps);
-        }
-        tc_fence_before();
-    };
-
-    // ---- P4: banded mel on the magnitude tile, log epilogue, stores
-    auto phase4 = [&](int i) {
-        long long b; int t0, s_first;
-        batch_geom(i, b, t0, s_first);
-        const int r = lane >> 3, t = lane & 7;
-        const float descale = s_descale[i & 3];
-        if (p.dbg_mag) {
-            for (int e = tid; e < kStcBins * kStcGroup; e += kStcThreads) {
-                const int bin = e >> 3, tt = e & 7;
-                if (t0 + tt < p.k.T) {
-                    float m = s_mag[(kStcMagPad + bin) * kStcGroup + tt] * descale;
-                    if (kPower == 2) m *= descale;
-                    p.dbg_mag[((long long)b * kStcBins + bin) * p.k.T + t0 + tt] = m;
-                }
-            }
-        }
-#pragma unroll 1
-        for (int s = 0; s < kStcMelSlots; ++s) {
-            const int g = s_grp[warp * kStcMelSlots + s];
-            if (g < 0) break;
-            const int2 ent = s_ent[g * 4 + r];
-            const int len = s_glen[g];
-            const float *w = s_melw + s_gwoff[g] + r;
-            const float *mg = s_mag + (kStcMagPad + ent.y) * kStcGroup + t;
-            float acc0 = 0.f, acc1 = 0.f;
-            int q = 0;
-#pragma unroll 4
-            for (; q + 1 < len; q += 2) {
-                acc0 = fmaf(w[4 * q], mg[kStcGroup * q], acc0);
-                acc1 = fmaf(w[4 * q + 4], mg[kStcGroup * q + kStcGroup], acc1);
-            }
-            if (q < len) acc0 = fmaf(w[4 * q], mg[kStcGroup * q], acc0);
-            float x = (acc0 + acc1) * descale;
-            if (kPower == 2) x *= descale;
-            if (ent.x >= 0 && t0 + t < p.k.T)
-                p.k.out_mel[((long long)b * p.k.n_mels + ent.x) * p.k.T + t0 + t] = epilogue(x, p.k);
-        }
-    };
-
-#ifdef B200MEL_STC_TIMING
-    // per-CTA phase accounting (tools/tc_bench.py --timing): thread 0's clock at the phase boundaries, summed over CTAs
-    long long stc_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    long long stc_mark = clock64();
-#define STC_MARK(i)                              \
-    do {                                         \
-        const long long now_ = clock64();        \
-        stc_acc[i] += now_ - stc_mark;           \
-        stc_mark = now_;                         \
-    } while (0)
-#else
-#define STC_MARK(i) \
-    do {            \
-    } while (0)
-#endif
-    // ------------------------------------------------------------------ the pipelined batch loop
-    if (n_mine > 0) {
-        if (tid == 0) {
-            issue_tma(0);
-            if (n_mine > 1) issue_tma(1);
-        }
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        phase1(0);
-        __syncthreads();
-        if (tid == 0) {
-            issue_m1();
-            if (n_mine > 2) issue_tma(2);
-        }
-        STC_MARK(0);
-        for (int i = 0; i < n_mine; ++i) {
-            mbar_wait(smem_u32(s_bar + 2), (uint32_t)i & 1u);                                 // D1(i) complete, S free
+        const float S = 1.0f / (float)(1 << kStcShift);
+        STC_TIMER();
+        for (int j = 0; j < n_mine; ++j) {
+            STC_MARK(0);
+            mbar_park(bar(kBarD1Full + (j & 1)), (uint32_t)(j >> 1) & 1u);
             STC_MARK(1);
-            if (i > 0) mbar_wait(smem_u32(s_bar + 3 + ((i - 1) & 1)), (uint32_t)((i - 1) >> 1) & 1u);  // M2(i-1) done: A2 free
+            if (j >= 2) mbar_park(bar(kBarD2Full + (j & 1)), (uint32_t)((j - 2) >> 1) & 1u);  // M2(j - 2) done: A2 buffer free
             tc_fence_after();
             STC_MARK(2);
-            phase2(i);
-            __syncthreads();
-            STC_MARK(3);
-            if (tid == 0) issue_m2(i);
-            STC_MARK(4);
-            if (i + 1 < n_mine) {
-                phase1(i + 1);
-                __syncthreads();
-                STC_MARK(5);
-                if (tid == 0) {
-                    issue_m1();
-                    if (i + 3 < n_mine) issue_tma(i + 3);
+            const uint32_t ta = tm_d1 + 128u * (uint32_t)(j & 1) + ((uint32_t)(32 * quad) << 16) + 64u * h;
+            unsigned char *dst = smem + kStcOffA2 + (j & 1) * 2 * kStcA2Bytes + t * 16 + (n2 >> 2) * 2048 + (n2 & 3) * 4;
+            float a[20], b2[20];
+            {   // a: columns 0..19 (A0, A16, A1..A9); b2: columns 16..31 (A8..A15) and 0..3 (A0, A16, A1); each as hi part + lo part
+                float l[20], l2[20];
+                tmem_ld16(ta, a), tmem_ld4(ta + 16, a + 16), tmem_ld16(ta + 32, l), tmem_ld4(ta + 48, l + 16);
+                tmem_ld16(ta + 16, b2), tmem_ld4(ta, b2 + 16), tmem_ld16(ta + 48, l2), tmem_ld4(ta + 32, l2 + 16);
+                tmem_ld_wait();
+                tc_fence_before();
+                warp_arrive(bar(kBarD1Empty + (j & 1)), lane);
+#pragma unroll
+                for (int c = 0; c < 20; c += 2) {
+                    const float2 u = __fadd2_rn(make_float2(a[c], a[c + 1]), make_float2(l[c], l[c + 1]));
+                    const float2 v = __fadd2_rn(make_float2(b2[c], b2[c + 1]), make_float2(l2[c], l2[c + 1]));
+                    a[c] = u.x, a[c + 1] = u.y, b2[c] = v.x, b2[c + 1] = v.y;
                 }
-                STC_MARK(6);
             }
-            if (i > 0) {
-                phase3(i - 1);
-                __syncthreads();
-                STC_MARK(7);
-                phase4(i - 1);
-                STC_MARK(8);
+            if (p.dbg_d1 && first == 0 && j == 0) {
+                float *d = p.dbg_d1 + (n2 * 8 + t) * 32;
+#pragma unroll
+                for (int c = 0; c < 20; ++c) d[c] = a[c];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) d[16 + c] = b2[c];
             }
+            {   // slots 1..8 from A'[0..9]
+                float2 ap[10];
+                ap[0] = make_float2(a[0] * S, 0.f);
+#pragma unroll
+                for (int k = 1; k < 10; ++k) ap[k] = cmul(make_float2(a[2 * k], a[2 * k + 1]), tw[32 * k]);
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    const float2 sum = __fadd2_rn(ap[o], ap[o + 2]);
+                    const float2 w = __ffma2_rn(sum, make_float2(-0.25f, -0.25f), __fmul2_rn(ap[o + 1], make_float2(0.5f, 0.5f)));
+                    uint32_t hi, lo;
+                    split_f16x2(w.x, w.y, hi, lo);
+                    *reinterpret_cast<uint32_t *>(dst + (o + 1) * 128) = hi;
+                    *reinterpret_cast<uint32_t *>(dst + kStcA2Bytes + (o + 1) * 128) = lo;
+                }
+            }
+            {   // slots 9..15 from A'[8..16], and the packed slot 0 = (Aw'[0], r16)
+                float2 ap[9];
+#pragma unroll
+                for (int k = 8; k < 16; ++k) ap[k - 8] = cmul(make_float2(b2[2 * (k - 8)], b2[2 * (k - 8) + 1]), tw[32 * k]);
+                const float2 w16 = tw[32 * 16], w1 = tw[32];
+                ap[8] = make_float2(b2[17] * w16.x, b2[17] * w16.y);                 // A'[16] = W^(16 n2) A[16], A[16] real
+                const float2 ap1 = cmul(make_float2(b2[18], b2[19]), w1);            // A'[1]
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    float2 w;
+                    if (o < 7) {
+                        const float2 sum = __fadd2_rn(ap[o], ap[o + 2]);
+                        w = __ffma2_rn(sum, make_float2(-0.25f, -0.25f), __fmul2_rn(ap[o + 1], make_float2(0.5f, 0.5f)));
+                    } else {
+                        w.x = 0.5f * S * b2[16] - 0.5f * ap1.x;                                 // Aw'[0] (real)
+                        w.y = 0.5f * S * b2[17] - 0.5f * fmaf(w1.x, b2[14], w1.y * b2[15]);     // r16: Aw'[16] = W64^n2 r16
+                    }
+                    const int slot = o < 7 ? o + 9 : 0;
+                    uint32_t hi, lo;
+                    split_f16x2(w.x, w.y, hi, lo);
+                    *reinterpret_cast<uint32_t *>(dst + slot * 128) = hi;
+                    *reinterpret_cast<uint32_t *>(dst + kStcA2Bytes + slot * 128) = lo;
+                }
+            }
+            fence_proxy_async();
+            warp_arrive(bar(kBarA2Full + (j & 1)), lane);
+            STC_MARK(3);
         }
-        mbar_wait(smem_u32(s_bar + 3 + ((n_mine - 1) & 1)), (uint32_t)((n_mine - 1) >> 1) & 1u);
-        tc_fence_after();
-        __syncthreads();   // P4(n-2) readers of the magnitude tile are done
-        phase3(n_mine - 1);
-        __syncthreads();
-        phase4(n_mine - 1);
+        if (warp == 0) STC_FLUSH(1);
+    } else if (warp < kStcTwWarps + kStcSpecWarps) {
+        // ================================================================== spectrum warps: P3
+        const int quad = warp & 3;
+        const int slot = 4 * quad + (lane >> 3), t = lane & 7;
+        const int off2 = slot ? 32 - slot : 16;
+        STC_TIMER();
+        for (int j = 0; j < n_mine; ++j) {
+            STC_MARK(0);
+            mbar_park(bar(kBarD2Full + (j & 1)), (uint32_t)(j >> 1) & 1u);
+            STC_MARK(1);
+            if (j >= 2) mbar_park(bar(kBarMagEmpty + (j & 1)), (uint32_t)((j - 2) >> 1) & 1u);
+            tc_fence_after();
+            STC_MARK(2);
+            const uint32_t ta = tm_d2 + ((uint32_t)(32 * quad) << 16);
+            float *tile = reinterpret_cast<float *>(smem + kStcOffMag + (j & 1) * kStcMagBytes);
+            const float descale = s_descale[j & 7];
+            const float eps = p.k.mag_eps > 0.f ? (p.k.mag_eps / descale) / descale : 0.f;
+#pragma unroll
+            for (int jq = 0; jq < 4; ++jq) {   // 6 complex outputs at a time: columns 12 jq .. 12 jq + 11 of the 48
+                float a[12], l[12];
+                const uint32_t col = 12u * jq;
+                tmem_ld8(ta + col, a), tmem_ld4(ta + col + 8, a + 8), tmem_ld8(ta + 96 + col, l), tmem_ld4(ta + 96 + col + 8, l + 8);
+                if (quad == 0) {  // rows 0..7 (lanes 0..7) are the packed rows: their results sit in the B' columns (+48)
+                    float a2[12], l2[12];
+                    tmem_ld8(ta + 48 + col, a2), tmem_ld4(ta + 48 + col + 8, a2 + 8);
+                    tmem_ld8(ta + 144 + col, l2), tmem_ld4(ta + 144 + col + 8, l2 + 8);
+                    tmem_ld_wait();
+                    if (lane < 8) {
+#pragma unroll
+                        for (int c = 0; c < 12; ++c) a[c] = a2[c], l[c] = l2[c];
+                    }
+                } else {
+                    tmem_ld_wait();
+                }
+                if (jq == 3) {
+                    tc_fence_before();
+                    warp_arrive(bar(kBarD2Empty), lane);
+                }
+#pragma unroll
+                for (int c = 0; c < 12; c += 2) {
+                    const float2 u = __fadd2_rn(make_float2(a[c], a[c + 1]), make_float2(l[c], l[c + 1]));
+                    a[c] = u.x, a[c + 1] = u.y;
+                }
+                if (p.dbg_d2 && first == 0 && j == 0) {
+                    float *d = p.dbg_d2 + (slot * 8 + t) * 48 + 12 * jq;
+#pragma unroll
+                    for (int c = 0; c < 12; ++c) d[c] = a[c];
+                }
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    const int jj = 6 * jq + c;
+                    const int bin = jq < 2 ? slot + 32 * jj : off2 + 32 * (23 - jj);
+                    tile[(kStcMagPad + bin) * kStcGroup + t] = magnitude<kPower>(a[2 * c], a[2 * c + 1], eps);
+                }
+            }
+            warp_arrive(bar(kBarMagFull + (j & 1)), lane);
+            STC_MARK(3);
+        }
+        if (warp == kStcTwWarps) STC_FLUSH(2);
+    } else if (warp < kStcTwWarps + kStcSpecWarps + kStcEdgeWarps) {
+        // ================================================================== edge warps: P1
+        // staged fp32 samples -> max |x| -> power-of-two scale -> fp16 limbs in the Hankel layout
+        const int e = warp - kStcTwWarps - kStcSpecWarps;
+        STC_TIMER();
+        for (int j = 0; j < n_mine; ++j) {
+            STC_MARK(0);
+            mbar_park(bar(kBarStageFull + (j & 1)), (uint32_t)(j >> 1) & 1u);
+            STC_MARK(1);
+            const int *geo = s_geo + (j & 1) * 8;
+            const int s_first = geo[1], delta = geo[2];
+            const float *st = reinterpret_cast<const float *>(smem + kStcOffStage + (j & 1) * kStcStageBytes) + delta - s_first;
+            float v[3][8];   // q octets e, e + 4, e + 8 (the last one only for e < 3)
+            if (geo[5] == 0) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    if (e + 4 * r < 11) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[r][i] = st[s_first + 256 * (e + 4 * r) + lane + 32 * i];
+                    }
+            } else {   // edge of the clip: reflected samples (and floats cut off by the tensor-edge clamp) come from global memory
+                const int c_lo = geo[3], c_hi = geo[4];
+                const float *row = p.k.wav + (long long)geo[0] * p.k.row_stride;
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    if (e + 4 * r < 11) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int sidx = s_first + 256 * (e + 4 * r) + lane + 32 * i;
+                            v[r][i] = (sidx >= c_lo && sidx < c_hi) ? st[sidx] : __ldg(row + reflect_index(sidx, p.k.L));
+                        }
+                    }
+            }
+            // max |x| on the bit patterns: NaN / Inf compare above every finite value and switch the scaling off
+            uint32_t m = 0u;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                if (e + 4 * r < 11) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) m = max(m, __float_as_uint(v[r][i]) & 0x7fffffffu);
+                }
+            warp_arrive(bar(kBarStageEmpty + (j & 1)), lane);
+            const uint32_t wm = __reduce_max_sync(0xffffffffu, m);
+            if (lane == 0) s_wmax[(j & 1) * 4 + e] = wm;
+            STC_MARK(2);
+            asm volatile("bar.sync 1, %0;" ::"n"(kStcEdgeWarps * 32) : "memory");
+            STC_MARK(3);
+            const uint4 all = *reinterpret_cast<const uint4 *>(s_wmax + (j & 1) * 4);
+            const uint32_t mx = max(max(all.x, all.y), max(all.z, all.w));
+            // power-of-two scale: max |x| * sc in [2^13, 2^14); 1 for silence / non-finite input
+            int sexp = 127;
+            if (mx != 0u && mx < 0x7f800000u) {
+                sexp = 267 - (int)(mx >> 23);
+                sexp = min(max(sexp, 1), 254);
+                if (p.k.mag_eps > 0.f) sexp = min(sexp, 127 + 40);
+            }
+            const float sc = __uint_as_float((uint32_t)sexp << 23);
+            if (e == 0 && lane == 0) s_descale[j & 7] = __uint_as_float((uint32_t)(260 - sexp) << 23);  // 2^6 / sc
+            if (j >= 2) mbar_park(bar(kBarD1Full + (j & 1)), (uint32_t)((j - 2) >> 1) & 1u);  // M1(j - 2) done: Hankel buffer free
+            STC_MARK(4);
+            unsigned char *hk = smem + kStcOffHank + (j & 1) * 2 * kStcHankBytes + lane * kStcPitch;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int oct = e + 4 * r;
+                if (oct < 11) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) split_f16x2(v[r][2 * i] * sc, v[r][2 * i + 1] * sc, hi[i], lo[i]);
+                    *reinterpret_cast<uint4 *>(hk + oct * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4 *>(hk + kStcHankBytes + oct * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+            fence_proxy_async();
+            warp_arrive(bar(kBarSFull + (j & 1)), lane);
+            STC_MARK(5);
+        }
+        if (e == 0) STC_FLUSH(3);
     } else {
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        // ================================================================== mel warps: P4
+        // one mel row per thread, all 8 frames of the batch in registers (a weight is loaded once per 8 FMAs); the
+        // results are transposed through a per-warp tile so that 8 lanes store the 32 contiguous bytes of a row
+        const int mw = warp - kStcTwWarps - kStcSpecWarps - kStcEdgeWarps;
+        const int2 ent = s_ent[mw * 32 + lane];                 // {mel row (-1: idle), first bin of the read window}
+        const int trip = s_trip[mw];
+        const float *wgt = s_melw + s_woff[mw] + lane;
+        float *otile = reinterpret_cast<float *>(smem + kStcOffOut + mw * kStcOutBytes);
+        const int r4 = lane >> 3, t = lane & 7;
+        STC_TIMER();
+        for (int j = 0; j < n_mine; ++j) {
+            STC_MARK(0);
+            unsigned b; int t0, s_first;
+            batch_geom(j, b, t0, s_first);
+            mbar_park(bar(kBarMagFull + (j & 1)), (uint32_t)(j >> 1) & 1u);
+            STC_MARK(1);
+            const float4 *tile = reinterpret_cast<const float4 *>(smem + kStcOffMag + (j & 1) * kStcMagBytes) + (kStcMagPad + ent.y) * 2;
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+#pragma unroll 4
+            for (int i = 0; i < trip; ++i) {
+                const float w = wgt[32 * i];
+                const float4 m0 = tile[2 * i], m1 = tile[2 * i + 1];
+                a0.x = fmaf(w, m0.x, a0.x), a0.y = fmaf(w, m0.y, a0.y), a0.z = fmaf(w, m0.z, a0.z), a0.w = fmaf(w, m0.w, a0.w);
+                a1.x = fmaf(w, m1.x, a1.x), a1.y = fmaf(w, m1.y, a1.y), a1.z = fmaf(w, m1.z, a1.z), a1.w = fmaf(w, m1.w, a1.w);
+            }
+            warp_arrive(bar(kBarMagEmpty + (j & 1)), lane);
+            if (p.dbg_mag && mw == 0) {   // debug tap: the whole magnitude tile of this batch
+                const float *tl = reinterpret_cast<const float *>(smem + kStcOffMag + (j & 1) * kStcMagBytes);
+                const float ds = s_descale[j & 7];
+                for (int el = lane; el < kStcBins * kStcGroup; el += 32) {
+                    const int bin = el >> 3, tt = el & 7;
+                    if (t0 + tt < p.k.T) {
+                        float m = tl[(kStcMagPad + bin) * kStcGroup + tt] * ds;
+                        if (kPower == 2) m *= ds;
+                        p.dbg_mag[((long long)b * kStcBins + bin) * p.k.T + t0 + tt] = m;
+                    }
+                }
+            }
+            *reinterpret_cast<float4 *>(otile + lane * kStcOutPitch) = a0;
+            *reinterpret_cast<float4 *>(otile + lane * kStcOutPitch + 4) = a1;
+            __syncwarp();
+            const float descale = s_descale[j & 7];
+            float *obase = p.k.out_mel + (long long)b * p.k.n_mels * p.k.T + t0 + t;
+            const bool t_ok = t0 + t < p.k.T;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int row = 4 * it + r4;
+                const int m = __shfl_sync(0xffffffffu, ent.x, row);
+                float x = otile[row * kStcOutPitch + t] * descale;
+                if (kPower == 2) x *= descale;
+                if (m >= 0 && t_ok) obase[(long long)m * p.k.T] = epilogue(x, p.k);
+            }
+            __syncwarp();
+            STC_MARK(2);
+        }
+        if (mw == 0) STC_FLUSH(4);
     }
     // ------------------------------------------------------------------ teardown
-#ifdef B200MEL_STC_TIMING
-    STC_MARK(9);
-    if (tid == 0 && p.k.dbg)
-        for (int i = 0; i < 10; ++i) atomicAdd(reinterpret_cast<unsigned long long *>(p.k.dbg) + i, (unsigned long long)stc_acc[i]);
-#endif
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    if (warp == kStcWorkWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
 }  // namespace b200mel

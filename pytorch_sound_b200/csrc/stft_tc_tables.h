@@ -45,7 +45,7 @@ static inline int stc_k2_of_j(int j) { return j < 12 ? j : j + 8; }
 // bin >= 384.  W is (n_mels, F) row-major in LOGICAL bins of the 1024-point transform (F = 513).
 static bool stc_build_tables(const float *W, int n_mels, int F, StcTables *out, const char **why) {
     const double two_pi = 6.283185307179586476925286766559;
-    if (n_mels < 1 || n_mels > 4 * kStcMaxGroups) { *why = "more than 128 mel rows"; return false; }
+    if (n_mels < 1 || n_mels > kStcMaxMels) { *why = "more than 128 mel rows"; return false; }
     struct Row { int m, first, last; };
     std::vector<Row> rows;
     for (int m = 0; m < n_mels; ++m) {
@@ -60,8 +60,6 @@ static bool stc_build_tables(const float *W, int n_mels, int F, StcTables *out, 
         rows.push_back({m, first, last});
     }
     std::stable_sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) { return a.last - a.first > b.last - b.first; });
-    while (rows.size() % 4) rows.push_back({-1, 0, 0});
-    const int NG = (int)rows.size() / 4;
 
     out->blob.assign(kStcB1Bytes + kStcB2Bytes + kStcTwBytes, 0);
     uint16_t *b1 = reinterpret_cast<uint16_t *>(out->blob.data());
@@ -116,55 +114,44 @@ static bool stc_build_tables(const float *W, int n_mels, int F, StcTables *out, 
             tw[(k1 * 32 + n2) * 2] = (float)(S * cos(ang));
             tw[(k1 * 32 + n2) * 2 + 1] = (float)(-S * sin(ang));
         }
-    // ---- mel schedule: groups of 4 rows (one per lane quarter), windows slid so the four rows of a group start at
-    //      bins = 0, 1, 2, 3 (mod 4) — their 32-byte tile rows then fall into different banks — and kept below bin 384
+    // ---- mel schedule: one row per thread of the mel warps, rows sorted by length (longest first) so that the rows of
+    //      a warp have similar lengths; every lane of warp v runs trip[v] bins.  Read windows are slid down so that
+    //      lane l starts at a bin = l (mod 4) — the 32-byte tile rows of neighbouring lanes then spread over the banks —
+    //      and kept below bin 384; weights are stored [warp][bin step][lane].
     std::vector<int> header(kStcMelHeader / 4, 0);
-    int *grp = header.data(), *glen = grp + 16 * kStcMelSlots, *gwoff = glen + kStcMaxGroups;
-    int *ent = gwoff + kStcMaxGroups;  // {m, lo} pairs
+    int *trip = header.data(), *woff = trip + kStcMelWarps, *ent = woff + kStcMelWarps;  // ent: {m, lo} pairs
     std::vector<float> w;
-    std::vector<int> lo(rows.size());
-    for (int g = 0; g < NG; ++g) {
-        int len = 1;
-        for (int r = 0; r < 4; ++r) {
-            const Row &row = rows[g * 4 + r];
-            int l = row.first - (((row.first - r) % 4) + 4) % 4;  // <= first, = r (mod 4), >= -3
-            lo[g * 4 + r] = l;
-            len = std::max(len, row.last - l + 1);
+    while ((int)rows.size() < kStcMaxMels) rows.push_back({-1, 0, 0});
+    for (int v = 0; v < kStcMelWarps; ++v) {
+        int lo[32], len = 0;
+        bool any = false;
+        for (int l = 0; l < 32; ++l) {
+            const Row &row = rows[v * 32 + l];
+            lo[l] = row.first - (((row.first - l) % 4) + 4) % 4;  // <= first, = l (mod 4), >= -3
+            if (row.m >= 0) any = true, len = std::max(len, row.last - lo[l] + 1);
         }
-        for (bool moved = true; moved;) {  // windows must end inside the tile: slide down in steps of 4
+        for (bool moved = any; moved;) {  // windows must end inside the tile: slide down in steps of 4
             moved = false;
-            for (int r = 0; r < 4; ++r)
-                while (lo[g * 4 + r] + len > kStcBins) {
-                    lo[g * 4 + r] -= 4;
-                    len = std::max(len, rows[g * 4 + r].last - lo[g * 4 + r] + 1);
+            for (int l = 0; l < 32; ++l)
+                while (lo[l] + len > kStcBins) {
+                    lo[l] -= 4;
+                    if (rows[v * 32 + l].m >= 0) len = std::max(len, rows[v * 32 + l].last - lo[l] + 1);
                     moved = true;
                 }
         }
-        glen[g] = len;
-        gwoff[g] = (int)w.size();
+        trip[v] = len;
+        woff[v] = (int)w.size();
         for (int i = 0; i < len; ++i)
-            for (int r = 0; r < 4; ++r) {
-                const Row &row = rows[g * 4 + r];
-                const int bin = lo[g * 4 + r] + i;
+            for (int l = 0; l < 32; ++l) {
+                const Row &row = rows[v * 32 + l];
+                const int bin = lo[l] + i;
                 w.push_back((row.m >= 0 && bin >= row.first && bin <= row.last) ? W[(size_t)row.m * F + bin] : 0.f);
             }
-        for (int r = 0; r < 4; ++r) ent[(g * 4 + r) * 2] = rows[g * 4 + r].m, ent[(g * 4 + r) * 2 + 1] = lo[g * 4 + r];
+        for (int l = 0; l < 32; ++l) ent[(v * 32 + l) * 2] = rows[v * 32 + l].m, ent[(v * 32 + l) * 2 + 1] = lo[l];
         out->max_len = std::max(out->max_len, len);
+        out->warp_cost_max = std::max(out->warp_cost_max, len);
     }
-    // longest-processing-time assignment of groups to the 16 warps
-    std::vector<int> order(NG), load(16, 0), cnt(16, 0);
-    for (int g = 0; g < NG; ++g) order[g] = g;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return glen[a] > glen[b]; });
-    for (int i = 0; i < 16 * kStcMelSlots; ++i) grp[i] = -1;
-    for (int g : order) {
-        int best = -1;
-        for (int wv = 0; wv < 16; ++wv)
-            if (cnt[wv] < kStcMelSlots && (best < 0 || load[wv] < load[best])) best = wv;
-        grp[best * kStcMelSlots + cnt[best]++] = g;
-        load[best] += glen[g] + 6;
-    }
-    out->warp_cost_max = *std::max_element(load.begin(), load.end());
-    out->n_groups = NG;
+    out->n_groups = kStcMelWarps;
     while (w.size() % 4) w.push_back(0.f);
     out->mel_bytes = kStcMelHeader + (int)w.size() * 4;
     const size_t base = out->blob.size();

@@ -95,31 +95,27 @@ def test_mel_schedule_replays_to_the_dense_filterbank(cfg):
     assert blob is not None, "filterbank below bin 384 must be eligible"
     mel = blob[4096 + 24576 + 17 * 32 * 8:]
     assert len(mel) == info[0] and info[0] % 16 == 0
-    hdr = mel[:1536].view(np.int32)
-    grp, glen, gwoff, ent = hdr[:64].reshape(16, 4), hdr[64:96], hdr[96:128], hdr[128:].reshape(128, 2)
-    w = mel[1536:].view(np.float32)
+    hdr = mel[:1056].view(np.int32)                      # trip[4] | woff[4] | ent[128] {m, lo}
+    trip, woff, ent = hdr[:4], hdr[4:8], hdr[8:].reshape(128, 2)
+    w = mel[1056:].view(np.float32)
     dense = np.zeros_like(W)
     seen = set()
-    for wv in range(16):
-        for s in range(4):
-            g = grp[wv, s]
-            if g < 0:
-                assert (grp[wv, s:] < 0).all()
-                break
-            assert g not in seen
-            seen.add(int(g))
-            los = ent[4 * g:4 * g + 4, 1]
-            assert sorted(int(x) % 4 for x in los) == [0, 1, 2, 3]      # four different banks
-            for r in range(4):
-                m, lo = ent[4 * g + r]
-                assert lo >= -4 and lo + glen[g] <= 384                 # stays inside the (padded) magnitude tile
-                for i in range(glen[g]):
-                    v = w[gwoff[g] + 4 * i + r]
-                    if v != 0:
-                        assert m >= 0 and 0 <= lo + i
-                        dense[m, lo + i] += v
-    assert len(seen) == info[1] == (n_mels + 3) // 4
+    for v in range(4):
+        for lane in range(32):
+            m, lo = ent[32 * v + lane]
+            assert lo % 4 == lane % 4                                   # neighbouring lanes start in different banks
+            assert lo >= -4 and lo + trip[v] <= 384                     # stays inside the (padded) magnitude tile
+            if m >= 0:
+                assert m not in seen
+                seen.add(int(m))
+            for i in range(trip[v]):
+                val = w[woff[v] + 32 * i + lane]
+                if val != 0:
+                    assert m >= 0 and lo + i >= 0
+                    dense[m, lo + i] += val
+    assert len(seen) == n_mels
     assert np.array_equal(dense, W)
+    assert trip[0] >= trip[1] >= trip[2] >= trip[3]                      # rows sorted by length: idle warps come last
 
 
 def test_filterbank_above_bin_384_is_not_eligible():

@@ -103,13 +103,17 @@ def timing():
     lib.b200mel_debug_set_tc_mode(1)
     from pytorch_sound_b200.models.transforms import LogMelSpectrogram
     m = LogMelSpectrogram(22050, 80, 1024, 1024, 256, -50, 30, 0., 8000.).cuda()
-    names = ["prologue (P1(0), M1 issue)", "wait M1(i)", "wait M2(i-1)", "P2 + sync", "issue M2", "P1 + sync", "issue M1 / TMA",
-             "P3 + sync", "P4", "tail"]
+    names = [["poll / idle", "TMA issue", "M2 issue (8 MMAs + commit)", "M1 issue (8 MMAs + commit)", "", "", "", ""],
+             ["loop", "wait D1 full (M1 done)", "wait A2 free (M2(j-2) done)", "P2 compute + stores", "", "", "", ""],
+             ["loop", "wait D2 full (M2 done)", "wait mag tile free", "P3 compute", "", "", "", ""],
+             ["loop", "wait stage (TMA)", "loads + max", "edge barrier", "scale + wait S free", "convert + stores", "", ""],
+             ["loop + geometry", "wait mag full", "P4 (mel, epilogue, stores)", "", "", "", "", ""]]
+    roles = ["issuer", "twiddle warp 0", "spectrum warp 8", "edge warp 12", "mel warp 16"]
     for B, L in ((256, 22050), (256, 88200)):
         x = torch.randn(B, L, device="cuda") * 0.1
         m(x)
         torch.cuda.synchronize()
-        dbg = torch.zeros(20, dtype=torch.int64, device="cuda")
+        dbg = torch.zeros(48, dtype=torch.int64, device="cuda")
         lib.b200mel_debug_set_buffer(dbg.data_ptr())
         m(x)
         torch.cuda.synchronize()
@@ -117,43 +121,13 @@ def timing():
         d = dbg.cpu().tolist()
         T = L // 256 + 1
         batches = B * ((T + 7) // 8)
-        print(f"B={B} L={L}: {batches} batches, {batches / 148:.2f} per CTA; cycles per batch (thread 0 of each CTA, summed / batches)")
-        tot = sum(d[:10])
-        for i in range(10):
-            print(f"   {names[i]:28s} {d[i] / batches:9.0f}  {100 * d[i] / tot:5.1f} %")
-        print(f"   total {tot / batches:9.0f} cycles per batch = {tot / 148 / 1.965e3:.1f} us per CTA")
-
-
-def probe():
-    import numpy as np
-    import torch
-    torch.zeros(1, device="cuda")
-    from pytorch_sound_b200 import _lib
-    lib = _lib.lib()
-    lib.b200mel_debug_mma_probe.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
-    K = 1024
-    cfgs = [  # name, a_off, a_lbo, a_sbo, b_off, b_lbo, b_sbo, n, chain
-        ("M1 hi   Hankel A (lbo 16, sbo 176)  N=64", 0, 16, 176, 64 * K, 1024, 128, 64, 32),
-        ("M1 lo   Hankel A (lbo 16, sbo 176)  N=32", 0, 16, 176, 64 * K, 1024, 128, 32, 32),
-        ("        Hankel A (lbo 16, sbo 256)  N=64", 0, 16, 256, 64 * K, 1024, 128, 64, 32),
-        ("        Hankel A (lbo 16, sbo 128)  N=64", 0, 16, 128, 64 * K, 1024, 128, 64, 32),
-        ("        canonical A (lbo 2048, sbo 128) N=64", 0, 2048, 128, 64 * K, 1024, 128, 64, 32),
-        ("        canonical A (lbo 2048, sbo 128) N=32", 0, 2048, 128, 64 * K, 1024, 128, 32, 32),
-        ("        canonical A (lbo 128, sbo 256) N=64", 0, 128, 256, 64 * K, 1024, 128, 64, 32),
-        ("M2 hi   canonical A, B lbo 3072     N=192", 0, 2048, 128, 64 * K, 3072, 128, 192, 32),
-        ("M2 lo   canonical A, B lbo 3072     N=96", 0, 2048, 128, 64 * K, 3072, 128, 96, 32),
-        ("        canonical A, B lbo 128 sbo 256 N=192", 0, 2048, 128, 64 * K, 128, 256, 192, 32),
-        ("        canonical A, B lbo 4096     N=256", 0, 2048, 128, 64 * K, 4096, 128, 256, 32),
-        ("        canonical A, B lbo 4096     N=128", 0, 2048, 128, 64 * K, 4096, 128, 128, 32),
-        ("        canonical A, chain 8        N=192", 0, 2048, 128, 64 * K, 3072, 128, 192, 8),
-        ("        canonical A, chain 1        N=192", 0, 2048, 128, 64 * K, 3072, 128, 192, 1),
-        ("        Hankel A, chain 1           N=64", 0, 16, 176, 64 * K, 1024, 128, 64, 1),
-    ]
-    arr = np.array([c[1:] for c in cfgs], dtype=np.uint32)
-    out = np.zeros((len(cfgs), 2), dtype=np.int64)
-    _lib.check(lib.b200mel_debug_mma_probe(arr.ctypes.data, len(cfgs), out.ctypes.data))
-    for c, o in zip(cfgs, out):
-        print(f"{c[0]:48s} chain {c[-1]:3d}: issue {o[0] / c[-1]:7.1f} clk/MMA   issue+complete {o[1] / c[-1]:7.1f} clk/MMA  (total {o[1]})")
+        print(f"B={B} L={L}: {batches} batches, {batches / 148:.2f} per CTA; cycles per batch (one warp per role, summed over CTAs / batches)")
+        for r in range(5):
+            tot = sum(d[8 * r:8 * r + 8])
+            print(f"  {roles[r]}: total {tot / batches:7.0f}")
+            for i in range(8):
+                if names[r][i]:
+                    print(f"     {names[r][i]:34s} {d[8 * r + i] / batches:8.0f}")
 
 
 if __name__ == "__main__":
