@@ -17,8 +17,7 @@
 //
 // CTA-shared tables (fetched once per CTA by four bulk copies on one mbarrier): inter-pass twiddles, window,
 // banded mel filterbank in a lane-balanced schedule (rows sorted by length, 32 rows per round, weights padded
-// to float4 groups).  Compile-time probes (-DB200MEL_X_*) produce deliberately wrong results and exist only
-// for tools/variant_bench.py (upper bounds on what a phase can cost).
+// to float4 groups).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -110,9 +109,6 @@ struct KParams {
     float *out_fmask;  // nullable (B, T): SpectrogramMasker frame mask, 1 iff t * hop - win_half < clip length
     int win_half;
     long long *dbg;  // phase-timing accumulators (debug builds only)
-#ifdef B200MEL_X_MELLITE_LDC
-    float xw[64];    // probe: weights read from the kernel-parameter constant bank
-#endif
     float mag_eps;
     // branch-free epilogue: y = min(max(lg2(max(x, floor) + offset) * log_scale, lo), hi) * norm_scale + norm_bias
     int use_log;
@@ -404,11 +400,7 @@ __device__ __forceinline__ void xpose_read_twiddle(float2 *a, const float2 *buf,
         for (int i = 0; i < kB / 2; ++i) v[i] = row[h * (kB / 2) + i];
 #pragma unroll
         for (int i = 0; i < kB / 2; ++i)
-#ifdef B200MEL_X_NOTW  // upper-bound probe: no twiddle-table loads (wrong results)
-            t[i] = make_float4(0.6f, 0.8f, 0.8f, -0.6f);
-#else
             t[i] = tw4[(h * (kB / 2) + i) * 32];
-#endif
 #pragma unroll
         for (int i = 0; i < kB / 2; ++i) {
             const int j = h * kB + 2 * i;
@@ -637,9 +629,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
         if (valid0) {
             PHASE_MARK(1);  // decode
             // -------------------------------------------------------------- stage -> registers, windowed
-#ifndef B200MEL_X_NOWAIT  // probe: how much of a task is spent waiting for its samples (wrong results)
             mbar_wait(bar, parity);
-#endif
             parity ^= 1;
             if ((d.flags & 4u) || p.preemph != 0.f) patch_halo(d);
             const float *x0 = stage + d.delta + lane;
@@ -682,9 +672,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
 
         int2 e_first = make_int2(0, -1);  // {lo, m} of the first mel round, fetched early so its latency hides under pass 2
         if (valid0) {
-#ifndef B200MEL_X_LATE_ENTRY
             e_first = reinterpret_cast<const int2 *>(s_ent)[lane];
-#endif
             PHASE_MARK(6);  // prefetch issue
             fft32(a);  // pass 2: lane = k1, FFT over n2 -> Z[k1 + 32 k2] at a[pos(k2)]
             PHASE_MARK(7);  // pass 2
@@ -750,98 +738,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
         PHASE_MARK(8);  // separation + magnitudes
 
         // ---------------------------------------------------------------------- banded mel + log epilogue
-#ifdef B200MEL_X_NOMEL  // upper-bound probe (tools/variant_bench.py): no filterbank, results are NOT mel values
-        if (valid0) {
-            float *orow = p.out_mel + (long long)d.b * p.n_mels * (long long)p.T + d.t0;
-            for (int m = lane; m < p.n_mels; m += 32) {
-                const float2 v = tile2[4 * m];
-                orow[m * p.T] = v.x;
-                if (valid1) orow[m * p.T + 1] = v.y;
-            }
-            __syncwarp();
-        }
-#elif defined(B200MEL_X_MELLITE)  // cost stand-in for a lane = frame cooperative mel (wrong results): per warp and
-        // round ~29 conflict-free LDS.32 + 29 broadcast LDS.64 + 29 FFMA2, 5 epilogues with row-contiguous stores
-        if (valid0) {
-            float *orow = p.out_mel + (long long)d.b * p.n_mels * (long long)p.T + d.t0;
-            const float *tl = reinterpret_cast<const float *>(region) + lane;
-            const float2 *wq = reinterpret_cast<const float2 *>(s_melw);
-            float v[32];
-            float2 w[32];
-#pragma unroll
-            for (int k = 0; k < 32; ++k) v[k] = tl[k * 34];
-#ifdef B200MEL_X_MELLITE_LDC
-#pragma unroll
-            for (int k = 0; k < 32; ++k) w[k] = make_float2(p.xw[(warp * 2 + k) & 63], p.xw[(warp * 2 + k + 1) & 63]);
-#else
-#pragma unroll
-            for (int k = 0; k < 32; ++k) w[k] = wq[warp * 8 + k];
-#endif
-            float y[5];
-#pragma unroll
-            for (int sgm = 0; sgm < 5; ++sgm) {
-                float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int k = sgm * 6; k < sgm * 6 + 6; ++k) acc = __ffma2_rn(make_float2(v[k], v[k]), w[k], acc);
-                y[sgm] = epilogue(acc.x + acc.y + v[31] * w[30 + (sgm & 1)].x, p);
-            }
-#pragma unroll
-            for (int sgm = 0; sgm < 5; ++sgm) {
-                const int m = warp * 5 + sgm;
-                if (lane < 2 && (lane == 0 || valid1)) orow[m * p.T + lane] = y[sgm];
-            }
-            __syncwarp();
-        }
-#else
         if (valid0) {
             float *orow = p.out_mel + (long long)d.b * p.n_mels * (long long)p.T + d.t0;
             const int2 *ent2 = reinterpret_cast<const int2 *>(s_ent) + lane;
             const float4 *wbase = reinterpret_cast<const float4 *>(s_melw) + lane;
             const unsigned char *tile_bytes = region;
-#ifdef B200MEL_X_LATE_ENTRY
-            int2 e = ent2[0];  // {lo, m}; the next round's entry is fetched while this one computes
-#else
-            int2 e = e_first;
-#endif
-#ifdef B200MEL_MEL_FIXED
-            // Experiment for the next round (tools/variant_bench.py "-DB200MEL_MEL_FIXED=0x731": one hex digit per
-            // round = its weight groups, here 7, 3, 1 — nvcc splits -D values at commas): when the plan's
-            // rounds match a compile-time signature, all rounds run as ONE straight-line block — every entry and every
-            // 128-bit load is visible to the scheduler at once, so the loads of the later rounds can be issued under
-            // the arithmetic of the first (fewer serial load->use points).  Other plans take
-            // the generic loop below.  Summation order inside a round differs from the chunked generic path.
-            constexpr unsigned kSig = B200MEL_MEL_FIXED;
-            constexpr int kFixRounds = kSig > 0xfffu ? 4 : kSig > 0xffu ? 3 : kSig > 0xfu ? 2 : 1;
-            constexpr int kFix[4] = {(int)((kSig >> (4 * (kFixRounds - 1))) & 15u), kFixRounds > 1 ? (int)((kSig >> (4 * (kFixRounds - 2))) & 15u) : 0,
-                                     kFixRounds > 2 ? (int)((kSig >> (4 * (kFixRounds - 3))) & 15u) : 0, kFixRounds > 3 ? (int)(kSig & 15u) : 0};
-            bool fixed_ok = p.mel_rounds == kFixRounds;
-#pragma unroll
-            for (int r = 0; r < kFixRounds; ++r) fixed_ok = fixed_ok && p.round_groups[r] == kFix[r];
-            if (fixed_ok) {
-                int2 ents[kFixRounds];
-                float acc[kFixRounds][2];
-                ents[0] = e;
-#pragma unroll
-                for (int r = 1; r < kFixRounds; ++r) ents[r] = ent2[r * 32];
-                static_for<0, kFixRounds>([&](auto r_) {
-                    constexpr int r = decltype(r_)::value;
-                    int wb = 0;  // float4 index of the round's weights: sum of the earlier rounds' groups x 32 lanes
-#pragma unroll
-                    for (int i = 0; i < r; ++i) wb += kFix[i] * 32;
-                    acc[r][0] = acc[r][1] = 0.f;
-                    mel_round<kPair, kFix[r]>(wbase + wb, tile_bytes + ents[r].x * (kPair ? 8 : 4), acc[r][0], acc[r][1]);
-                });
-#pragma unroll
-                for (int r = 0; r < kFixRounds; ++r) {
-                    const float y0 = epilogue(acc[r][0], p), y1 = epilogue(acc[r][1], p);
-                    if (ents[r].y >= 0) {
-                        float *o = orow + ents[r].y * p.T;
-                        o[0] = y0;
-                        if (kPair && valid1) o[1] = y1;
-                    }
-                }
-            } else
-#endif
+            int2 e = e_first;  // {lo, m}; the next round's entry is fetched while this one computes
 #pragma unroll 1
             for (int r = 0; r < p.mel_rounds; ++r) {
                 const int2 ce = e;
@@ -862,7 +764,6 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
             __syncwarp();  // tile reads done before the next task's transpose overwrites the region
             PHASE_MARK(13);  // final syncwarp
         }
-#endif
     }
 #ifdef B200MEL_PHASE_TIMING
     if (p.dbg && lane == 0) {

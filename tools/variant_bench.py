@@ -1,12 +1,13 @@
 #!/usr/bin/env python
 """A/B timing of compile-time kernel variants (GPU box only).
 
-    python tools/variant_bench.py "" "-DB200MEL_X_NOMEL" "-DFOO -DBAR" ...
+    python tools/variant_bench.py "" "-DB200MEL_WARPS_PER_CTA=12" "ENV:B200MEL_NO_FAST=1" "ENV:B200MEL_TC=1" ...
 
 Every argument is a set of extra nvcc flags; each variant is built into gpurun_out/ (the shipped .so is untouched),
 loaded in a fresh subprocess and timed the way bench.py times `value`: a CUDA graph of 8 launches over 8 distinct
-C2 batches (256 x 22050), replayed, CUDA events.  Prints us per launch; variants marked X_ are experiments whose
-output is NOT checked (upper-bound probes), everything else is compared with the default build's output."""
+C2 batches (256 x 22050), replayed, CUDA events.  Prints us per launch and the largest difference from the default
+build's output.  (The upper-bound probes of round 1 — no filterbank, no twiddle loads, ... — were removed from the kernel
+after their results went into DESIGN.md section 4.)"""
 import os
 import subprocess
 import sys
