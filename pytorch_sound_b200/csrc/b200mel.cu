@@ -208,7 +208,7 @@ static int layout_smem(b200mel_plan *pl) {
             const int cols = L.warps * L.rt * (pl->pair ? 2 : 1);
             L.off_bar = pl->off_window + n_fft * 4;
             L.off_slots = L.off_bar + L.warps * 8;
-            L.off_regions = (L.off_slots + L.warps * L.rt * (int)sizeof(SpecSlot) + 127) & ~127;
+            L.off_regions = (L.off_slots + 2 * L.warps * L.rt * (int)sizeof(SpecSlot) + 127) & ~127;  // two sets: this round's and the one being written out
             L.off_tiles = L.off_regions + L.warps * L.region;
             L.smem = L.off_tiles + n_tiles * pl->phys_n_freq * (cols + 1) * 4;
             if (L.smem <= kMaxSmem) {
