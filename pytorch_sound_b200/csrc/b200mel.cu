@@ -142,10 +142,11 @@ struct b200mel_plan {
     // shared-memory layout
     int off_window = 0, off_entries = 0, off_melw = 0, off_bar = 0, off_regions = 0, region_bytes = 0, stage_bytes = 0;
     int n_warps = 0, smem_bytes = 0;
-    // spectrum-output kernel (spec_kernel.cuh): tw | window | mbarriers | slots | warp regions | tile A | tile B;
-    // one layout per output kind (index = B200MEL_SPEC_*): |X| only runs 16 warps x 1 task, two outputs 8 warps x 2 tasks
+    // spectrum-output kernel (spec_kernel.cuh): tw | window | mbarriers | slots | warp regions | per group: tile A (| tile B);
+    // one layout per output kind (index = B200MEL_SPEC_*): as many warp groups (4 warps in pair mode, 8 in split mode)
+    // as fit next to their tiles — |X| only: 4 groups, two outputs: 3 (pair mode, hop 256)
     struct SpecLayout {
-        int warps = 0, rt = 0, region = 0, off_bar = 0, off_slots = 0, off_regions = 0, off_tiles = 0, smem = 0;
+        int groups = 0, warps = 0, region = 0, off_bar = 0, off_slots = 0, off_regions = 0, off_tiles = 0, smem = 0;
     } sp[4];
     // staging for forward_host: one (input, output) pair per CUDA stream that has called it, so calls on different
     // streams overlap (copy of one batch under the kernel / read-back of another); calls on one stream are ordered
@@ -195,22 +196,20 @@ static int layout_smem(b200mel_plan *pl) {
         return fail(B200MEL_EUNSUP, "plan: hop_length / filterbank too large for the shared-memory staging of this build");
     pl->n_warps = n_warps;
     pl->smem_bytes = pl->off_regions + n_warps * pl->region_bytes;
-    // spectrum-output kernel: per output kind the widest (warps x tasks-per-round) shape that fits in shared memory
+    // spectrum-output kernel: per output kind as many warp groups as fit in shared memory (at most 16 warps)
     const int sp_region = (std::max(kXposeBytes, pl->stage_bytes) + 127) & ~127;  // stage overlaid on the transpose buffer
+    const int gw = pl->pair ? 4 : 8;
     for (int kind = 1; kind <= 3; ++kind) {
         const int n_tiles = kind == B200MEL_SPEC_MAG ? 1 : 2;
-        static const int shapes[3][2] = {{16, 1}, {8, 2}, {8, 1}};
         b200mel_plan::SpecLayout best;
-        for (const auto &sh : shapes) {
-            if (kind != B200MEL_SPEC_MAG && sh[0] == 16) continue;  // two tiles never fit next to 16 warp regions
+        for (int groups = 16 / gw; groups >= 1; --groups) {
             b200mel_plan::SpecLayout L;
-            L.warps = sh[0], L.rt = sh[1], L.region = sp_region;
-            const int cols = L.warps * L.rt * (pl->pair ? 2 : 1);
+            L.groups = groups, L.warps = groups * gw, L.region = sp_region;
             L.off_bar = pl->off_window + n_fft * 4;
             L.off_slots = L.off_bar + L.warps * 8;
-            L.off_regions = (L.off_slots + 2 * L.warps * L.rt * (int)sizeof(SpecSlot) + 127) & ~127;  // two sets: this round's and the one being written out
+            L.off_regions = (L.off_slots + 2 * L.warps * (int)sizeof(SpecSlot) + 127) & ~127;  // two sets: this round's and the one being written out
             L.off_tiles = L.off_regions + L.warps * L.region;
-            L.smem = L.off_tiles + n_tiles * pl->phys_n_freq * (cols + 1) * 4;
+            L.smem = L.off_tiles + groups * n_tiles * pl->phys_n_freq * 8 * 4;
             if (L.smem <= kMaxSmem) {
                 best = L;
                 break;
@@ -419,15 +418,31 @@ static kernel_fn pick_kernel(bool pair, int spec, bool mel, int power, int top_g
     return nullptr;
 }
 template <bool kPair, int kSpec>
-static kernel_fn pick_spec_shape(int warps, int rt) {
-    if (warps == 16) return spec_kernel<kPair, kSpec, 16, 1>;
-    return rt == 2 ? spec_kernel<kPair, kSpec, 8, 2> : spec_kernel<kPair, kSpec, 8, 1>;
+static kernel_fn pick_spec_shape(int groups) {
+    if constexpr (kPair) {
+        switch (groups) {
+            case 4: return spec_kernel<true, kSpec, 4>;
+            case 3: return spec_kernel<true, kSpec, 3>;
+            case 2: return spec_kernel<true, kSpec, 2>;
+            default: return spec_kernel<true, kSpec, 1>;
+        }
+    } else {
+        return groups >= 2 ? spec_kernel<false, kSpec, 2> : spec_kernel<false, kSpec, 1>;
+    }
 }
-static kernel_fn pick_spec_kernel(bool pair, int spec, int warps, int rt) {
+// compile-time specialised instance for the common geometry (see pick_fast_kernel) of the |X|-only kernel at the
+// group count the shared-memory layout gives that geometry.  Measured at C2: 36.8 -> 34.8 us; the same
+// specialisation of the two-output kernels (3 groups, 168 registers) measured SLOWER (61 -> 68 us, 54 -> 68 us)
+// and is not instantiated.
+static kernel_fn pick_spec_fast(int spec, int groups) {
+    if (spec == B200MEL_SPEC_MAG && groups == 4) return spec_kernel<true, B200MEL_SPEC_MAG, 4, true>;
+    return nullptr;
+}
+static kernel_fn pick_spec_kernel(bool pair, int spec, int groups) {
     switch (spec) {
-        case B200MEL_SPEC_MAG_PHASE: return pair ? pick_spec_shape<true, 1>(warps, rt) : pick_spec_shape<false, 1>(warps, rt);
-        case B200MEL_SPEC_RE_IM: return pair ? pick_spec_shape<true, 2>(warps, rt) : pick_spec_shape<false, 2>(warps, rt);
-        default: return pair ? pick_spec_shape<true, 3>(warps, rt) : pick_spec_shape<false, 3>(warps, rt);
+        case B200MEL_SPEC_MAG_PHASE: return pair ? pick_spec_shape<true, 1>(groups) : pick_spec_shape<false, 1>(groups);
+        case B200MEL_SPEC_RE_IM: return pair ? pick_spec_shape<true, 2>(groups) : pick_spec_shape<false, 2>(groups);
+        default: return pair ? pick_spec_shape<true, 3>(groups) : pick_spec_shape<false, 3>(groups);
     }
 }
 
@@ -663,8 +678,12 @@ int b200mel_plan_create(const b200mel_config *cfg, b200mel_plan **out) {
             for (int top = 12; top <= 16 && e == cudaSuccess; top += 4)
                 e = cudaFuncSetAttribute(pick_kernel(pl->pair, 0, true, power, top), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         for (int spec = 1; spec <= 3 && e == cudaSuccess; ++spec)
-            e = cudaFuncSetAttribute(pick_spec_kernel(pl->pair, spec, pl->sp[spec].warps, pl->sp[spec].rt),
+        {
+            e = cudaFuncSetAttribute(pick_spec_kernel(pl->pair, spec, pl->sp[spec].groups),
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+            if (kernel_fn ff = pl->pair ? pick_spec_fast(spec, pl->sp[spec].groups) : nullptr)
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(ff, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        }
         for (const FastEntry &fe : g_fast)
             if (e == cudaSuccess) e = cudaFuncSetAttribute(fe.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute (is the library built for this GPU?)"); break; }
@@ -880,13 +899,12 @@ int b200mel_forward_io(const b200mel_plan *pl, const b200mel_io *io, const b200m
     if (spec_kind && le == cudaSuccess) {
         // cooperative kernel with its own shared-memory carve-up and launch shape (per output kind)
         const b200mel_plan::SpecLayout &L = pl->sp[spec_kind];
-        const int round_tasks = L.warps * L.rt;
-        long long s_cta = (p.n_tasks + round_tasks - 1) / round_tasks;
+        const int cta_tasks = L.warps;  // one task per warp and round
+        long long s_cta = (p.n_tasks + cta_tasks - 1) / cta_tasks;
         if (s_cta > pl->num_sms) s_cta = pl->num_sms;
-        // a warp's jump from the last sub-task of a round to the first of its next round
-        const long long jump = s_cta * round_tasks - (long long)(L.rt - 1) * L.warps;
-        p.stride_b = (int)(jump / tpc);
-        p.stride_q = (int)(jump % tpc);
+        const long long step = s_cta * cta_tasks;  // between a warp's consecutive tasks
+        p.stride_b = (int)(step / tpc);
+        p.stride_q = (int)(step % tpc);
         p.off_bar = L.off_bar;
         p.off_entries = L.off_slots;
         p.off_regions = L.off_regions;
@@ -895,7 +913,12 @@ int b200mel_forward_io(const b200mel_plan *pl, const b200mel_io *io, const b200m
         cfg.gridDim = dim3((unsigned)s_cta);
         cfg.blockDim = dim3(L.warps * 32);
         cfg.dynamicSmemBytes = L.smem;
-        le = cudaLaunchKernelEx(&cfg, pick_spec_kernel(pl->pair, spec_kind, L.warps, L.rt), p);
+        kernel_fn sfn = nullptr;
+        if (!g_no_fast && !lengths && pl->pair && pl->pair_frames == 2 && pl->cfg.hop_length == kFastHop && pl->cfg.n_fft == pl->phys_n_fft &&
+            pl->cfg.win_length == pl->phys_n_fft && !g_table_window)
+            sfn = pick_spec_fast(spec_kind, L.groups);
+        if (!sfn) sfn = pick_spec_kernel(pl->pair, spec_kind, L.groups);
+        le = cudaLaunchKernelEx(&cfg, sfn, p);
         g_launches.fetch_add(1);
     }
     if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx");
