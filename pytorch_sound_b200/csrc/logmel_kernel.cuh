@@ -755,7 +755,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
                 const float y0 = epilogue(acc0, p), y1 = epilogue(acc1, p);
                 PHASE_MARK(11);  // log epilogue
                 if (ce.y >= 0) {
-                    float *o = orow + ce.y * p.T;
+                    float *o = orow + (long long)ce.y * p.T;
                     o[0] = y0;
                     if (kPair && valid1) o[1] = y1;
                 }
