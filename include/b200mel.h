@@ -151,8 +151,15 @@ int b200mel_forward(const b200mel_plan *plan, const float *wav, int64_t B, int64
  *                   [t*hop - win/2, t*hop + win/2) contains a valid sample or left padding, i.e.
  *                   t*hop - win_length/2 < lengths[b] (all ones without `lengths`).  Written by the same launch
  *                   as the mel frames (centre framing only).
+ *   out_mfcc        nullable device pointer float32 (B, n_mfcc, T): MelToMFCC.forward / MFCC.forward
+ *                   (models/transforms.py:419-455) fused as an epilogue of the mel launch — `dct_mat` (n_mfcc, n_mels)
+ *                   row-major, the module's registered buffer, is applied to the log-mel column of every frame while
+ *                   it is still on chip.  out_mel may then be NULL (the mel frames are never written).  Served by the
+ *                   compile-time specialised kernel only (n_fft = win_length = 1024, hop 256, no `lengths`, no frame
+ *                   mask / pre-emphasis / spectrum outputs, a log epilogue, n_mfcc <= 64): any other call returns
+ *                   B200MEL_EUNSUP and the caller runs b200mel_mel_to_mfcc on the mel output instead.
  * b200mel_forward(plan, wav, B, L, row_stride, lengths, epi, out_mel, spec_kind, out_a, out_b, stream) is exactly
- * b200mel_forward_io with out_frame_mask = NULL, reserve_sms = 0, preemphasis = 0. */
+ * b200mel_forward_io with out_frame_mask = NULL, reserve_sms = 0, preemphasis = 0, out_mfcc = NULL. */
 typedef struct b200mel_io {
     int32_t struct_size; /* = sizeof(b200mel_io) */
     int32_t spec_kind;   /* B200MEL_SPEC_* */
@@ -168,6 +175,10 @@ typedef struct b200mel_io {
     float preemphasis;   /* != 0: y[n] = x[n] - preemphasis * x[n-1] with the reference's 1-sample reflect pad (y[0] = x[0] -
                             preemphasis * x[1]) applied to the samples as they are staged, before framing — PreEmphasis.forward
                             (models/sound.py:66-81) fused as a prologue of the mel launch */
+    const float *dct_mat; /* (n_mfcc, n_mels) row-major, device; read when out_mfcc != NULL */
+    float *out_mfcc;
+    int32_t n_mfcc;
+    int32_t reserved0;    /* must be 0 */
 } b200mel_io;
 int b200mel_forward_io(const b200mel_plan *plan, const b200mel_io *io, const b200mel_epilogue *epi, void *stream);
 

@@ -39,6 +39,7 @@ class IO(C.Structure):
         ("struct_size", C.c_int32), ("spec_kind", C.c_int32), ("wav", C.c_void_p), ("B", C.c_int64), ("L", C.c_int64),
         ("row_stride", C.c_int64), ("lengths", C.c_void_p), ("out_mel", C.c_void_p), ("out_a", C.c_void_p),
         ("out_b", C.c_void_p), ("out_frame_mask", C.c_void_p), ("reserve_sms", C.c_int32), ("preemphasis", C.c_float),
+        ("dct_mat", C.c_void_p), ("out_mfcc", C.c_void_p), ("n_mfcc", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

@@ -448,8 +448,8 @@ static kernel_fn pick_spec_kernel(bool pair, int spec, int groups) {
 
 // Fast-path instantiations (logmel_fast.cuh): {bins < 384, all bins} x round signatures of the filterbanks the
 // reference's defaults and the BASELINE configs produce.  A plan whose signature is not listed uses the generic kernel.
-struct FastEntry { int top; unsigned sig; int power; kernel_fn fn; };
-#define B200MEL_FAST(top, sig) {top, sig, 1, logmel_fast_kernel<top, sig, 1>}
+struct FastEntry { int top; unsigned sig; int power; kernel_fn fn, fn_dct; };
+#define B200MEL_FAST(top, sig) {top, sig, 1, logmel_fast_kernel<top, sig, 1>, logmel_fast_kernel<top, sig, 1, true>}
 static const FastEntry g_fast[] = {
     B200MEL_FAST(12, 0x731u),  // 22050 Hz / 1024 / 80 mels / 0-8000 Hz: settings.py, C2, C3, HiFi-GAN front-end
     B200MEL_FAST(16, 0xa32u),  // 16000 Hz / 1024 / 80 mels / 0-8000 Hz: C5
@@ -466,13 +466,13 @@ static unsigned plan_signature(const b200mel_plan *pl) {
     return sig;
 }
 static const bool g_no_fast = getenv("B200MEL_NO_FAST") != nullptr;  // A/B: always run the generic kernel
-static kernel_fn pick_fast_kernel(const b200mel_plan *pl) {
-    if (g_no_fast || !pl->pair || pl->pair_frames != 2 || pl->cfg.hop_length != kFastHop || pl->cfg.win_length != pl->phys_n_fft ||
+static kernel_fn pick_fast_kernel(const b200mel_plan *pl, bool dct = false) {
+    if ((g_no_fast && !dct) || !pl->pair || pl->pair_frames != 2 || pl->cfg.hop_length != kFastHop || pl->cfg.win_length != pl->phys_n_fft ||
         pl->cfg.n_mels <= 0 || g_table_window || pl->n_warps != kMaxWarps)
         return nullptr;
     const unsigned sig = plan_signature(pl);
     for (const FastEntry &e : g_fast)
-        if (e.top == pl->top_groups && e.sig == sig && e.power == pl->cfg.power) return e.fn;
+        if (e.top == pl->top_groups && e.sig == sig && e.power == pl->cfg.power) return dct ? e.fn_dct : e.fn;
     return nullptr;
 }
 
@@ -684,8 +684,10 @@ int b200mel_plan_create(const b200mel_config *cfg, b200mel_plan **out) {
             if (kernel_fn ff = pl->pair ? pick_spec_fast(spec, pl->sp[spec].groups) : nullptr)
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(ff, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         }
-        for (const FastEntry &fe : g_fast)
+        for (const FastEntry &fe : g_fast) {
             if (e == cudaSuccess) e = cudaFuncSetAttribute(fe.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(fe.fn_dct, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        }
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute (is the library built for this GPU?)"); break; }
     } while (0);
     if (rc) {
@@ -766,7 +768,13 @@ int b200mel_forward_io(const b200mel_plan *pl, const b200mel_io *io, const b200m
     if (spec_kind && !out_a) return fail(B200MEL_EINVAL, "forward: spec_kind set but out_a is null");
     if ((spec_kind == B200MEL_SPEC_MAG_PHASE || spec_kind == B200MEL_SPEC_RE_IM) && !out_b)
         return fail(B200MEL_EINVAL, "forward: spec_kind needs out_b");
-    if (!out_mel && !spec_kind) return fail(B200MEL_EINVAL, "forward: no output requested");
+    if (io->reserved0 != 0) return fail(B200MEL_EINVAL, "forward: io.reserved0 must be 0");
+    if (io->out_mfcc) {
+        if (!io->dct_mat || io->n_mfcc < 1) return fail(B200MEL_EINVAL, "forward: out_mfcc needs dct_mat and n_mfcc >= 1");
+        if (pl->cfg.n_mels == 0) return fail(B200MEL_EINVAL, "forward: plan has no filterbank (n_mels = 0)");
+        if (!epi) return fail(B200MEL_EINVAL, "forward: mel output needs an epilogue");
+    }
+    if (!out_mel && !spec_kind && !io->out_mfcc) return fail(B200MEL_EINVAL, "forward: no output requested");
     if (out_mel && pl->cfg.n_mels == 0) return fail(B200MEL_EINVAL, "forward: plan has no filterbank (n_mels = 0)");
     if (out_mel && !epi) return fail(B200MEL_EINVAL, "forward: mel output needs an epilogue");
     if (epi && epi->struct_size != (int32_t)sizeof(b200mel_epilogue))
@@ -868,7 +876,25 @@ int b200mel_forward_io(const b200mel_plan *pl, const b200mel_io *io, const b200m
     cfg.numAttrs = 1;
     cudaError_t le = cudaSuccess;
     // mel and spectrum outputs come from separately specialised kernels (no reference module needs both at once)
-    if (out_mel && stc_enabled(pl, T, B) && !lengths && !p.out_fmask && p.preemph == 0.f && !spec_kind) {
+    if (io->out_mfcc) {
+        // MFCC as a fused epilogue of the compile-time specialised kernel; everything else is the caller's two launches
+        kernel_fn fn = (!lengths && p.use_log && !p.out_fmask && p.preemph == 0.f && !spec_kind && io->n_mfcc <= kDctPitch)
+                           ? pick_fast_kernel(pl, true) : nullptr;
+        const int dct_rows = (pl->cfg.n_mels + 1) & ~1;
+        p.dct = io->dct_mat, p.out_mfcc = io->out_mfcc, p.n_mfcc = io->n_mfcc;
+        p.off_dct = (pl->smem_bytes + 127) & ~127;
+        p.off_col = p.off_dct + dct_rows * kDctPitch * 4;
+        p.col_bytes = (dct_rows * 8 + 127) & ~127;
+        const int smem = p.off_col + pl->n_warps * p.col_bytes;
+        if (!fn || smem > kMaxSmem)
+            return fail(B200MEL_EUNSUP, "forward: the fused MFCC epilogue serves n_fft = win_length = 1024, hop 256, no lengths / "
+                                        "frame mask / pre-emphasis, n_mfcc <= 64 — run b200mel_mel_to_mfcc on the mel output instead");
+        cfg.gridDim = dim3((unsigned)n_cta);
+        cfg.blockDim = dim3(pl->n_warps * 32);
+        cfg.dynamicSmemBytes = smem;
+        le = cudaLaunchKernelEx(&cfg, fn, p);
+        g_launches.fetch_add(1);
+    } else if (out_mel && stc_enabled(pl, T, B) && !lengths && !p.out_fmask && p.preemph == 0.f && !spec_kind) {
         // both DFT stages on the tensor cores (stft_tc.cuh)
         StcParams sp;
         memset(&sp, 0, sizeof(sp));

@@ -81,9 +81,14 @@ __host__ __device__ constexpr int fast_sig_wbase(unsigned sig, int r) {  // floa
     return wb;
 }
 
+constexpr int kDctPitch = 64;  // floats per mel row of the shared DCT matrix: {coefficient lane, coefficient 32 + lane} at 2 * lane
+
 // kSig: one hex digit per mel round = its float4 weight groups (e.g. 0x731: three rounds of 7, 3 and 1 groups — the
 // settings.py filterbank 22050 Hz / 1024 / 80 mels / 0-8000 Hz).  kTop: 32-bin groups separated (12: bins < 384).
-template <int kTop, unsigned kSig, int kPower>
+// kDct: MelToMFCC / MFCC (models/transforms.py:419-455) fused as an epilogue — the lanes leave their log-mel values
+// of the two frames in a per-warp column, and lane c then forms coefficients c and 32 + c of both frames from the
+// shared DCT matrix (one broadcast 128-bit load of two column entries per four FFMA2).
+template <int kTop, unsigned kSig, int kPower, bool kDct = false>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_fast_kernel(const KParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -141,6 +146,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_fast_kernel(const KP
     __syncwarp();
     if (task < p.n_tasks) cur = fast_request(p, cb, cq, lane, stage_s, bar);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int dct_rows = (p.n_mels + 1) & ~1;
+    float *s_dct = reinterpret_cast<float *>(smem_raw + p.off_dct);
+    float2 *col = reinterpret_cast<float2 *>(smem_raw + p.off_col + warp * p.col_bytes);
+    if constexpr (kDct) {   // the DCT matrix is caller memory: after griddepcontrol.wait
+        for (int i = threadIdx.x; i < dct_rows * kDctPitch; i += blockDim.x) {
+            const int m = i / kDctPitch, c = ((i & 1) << 5) | ((i % kDctPitch) >> 1);   // pairs {lane, 32 + lane}
+            s_dct[i] = (m < p.n_mels && c < p.n_mfcc) ? __ldg(p.dct + (long long)c * p.n_mels + m) : 0.f;
+        }
+        if (lane == 0) col[dct_rows - 1] = make_float2(0.f, 0.f);  // the padding entry of an odd mel count
+    }
     __syncthreads();
     mbar_wait(tbar, 0);
 
@@ -215,12 +230,54 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_fast_kernel(const KP
             mel_groups<true, B200MEL_MEL_CHUNK>(fast_sig_groups(kSig, r), wbase + fast_sig_wbase(kSig, r), region + ents[r].x * 8, acc0, acc1);
             const float y0 = fast_epilogue(acc0, p), y1 = fast_epilogue(acc1, p);
             if (ents[r].y >= 0) {
-                float *o = orow + (long long)ents[r].y * p.T;
-                o[0] = y0;
-                if (valid1) o[1] = y1;
+                if constexpr (kDct) col[ents[r].y] = make_float2(y0, y1);
+                if (!kDct || p.out_mel) {
+                    float *o = orow + (long long)ents[r].y * p.T;
+                    o[0] = y0;
+                    if (valid1) o[1] = y1;
+                }
             }
         });
         __syncwarp();  // tile reads done before the next task's transpose overwrites the region
+        if constexpr (kDct) {
+            // coefficients lane (c0) and 32 + lane (c1) of frames t0, t0 + 1; two accumulators each (even / odd mel rows)
+            // halve the dependent FFMA2 chains
+            float2 c0 = make_float2(0.f, 0.f), c1 = c0, e0 = c0, e1 = c0;
+            const float2 *dl = reinterpret_cast<const float2 *>(s_dct) + lane;
+            if (p.n_mfcc > 32) {
+#pragma unroll 4
+                for (int m = 0; m < dct_rows; m += 2) {
+                    const float4 y = *reinterpret_cast<const float4 *>(col + m);   // {mel m: t0, t0+1, mel m+1: t0, t0+1}
+                    const float2 da = dl[m * (kDctPitch / 2)], db = dl[(m + 1) * (kDctPitch / 2)];
+                    c0 = __ffma2_rn(make_float2(da.x, da.x), make_float2(y.x, y.y), c0);
+                    c1 = __ffma2_rn(make_float2(da.y, da.y), make_float2(y.x, y.y), c1);
+                    e0 = __ffma2_rn(make_float2(db.x, db.x), make_float2(y.z, y.w), e0);
+                    e1 = __ffma2_rn(make_float2(db.y, db.y), make_float2(y.z, y.w), e1);
+                }
+            } else {
+                const float *ds = s_dct + 2 * lane;
+#pragma unroll 4
+                for (int m = 0; m < dct_rows; m += 2) {
+                    const float4 y = *reinterpret_cast<const float4 *>(col + m);
+                    c0 = __ffma2_rn(make_float2(ds[m * kDctPitch], ds[m * kDctPitch]), make_float2(y.x, y.y), c0);
+                    e0 = __ffma2_rn(make_float2(ds[(m + 1) * kDctPitch], ds[(m + 1) * kDctPitch]), make_float2(y.z, y.w), e0);
+                }
+            }
+            c0 = __fadd2_rn(c0, e0);
+            c1 = __fadd2_rn(c1, e1);
+            float *oc = p.out_mfcc + (long long)d.b * p.n_mfcc * (long long)p.T + d.t0;
+            if (lane < p.n_mfcc) {
+                float *o = oc + (long long)lane * p.T;
+                o[0] = c0.x;
+                if (valid1) o[1] = c0.y;
+            }
+            if (lane + 32 < p.n_mfcc) {
+                float *o = oc + (long long)(lane + 32) * p.T;
+                o[0] = c1.x;
+                if (valid1) o[1] = c1.y;
+            }
+            __syncwarp();  // column reads done before the next task's mel rounds rewrite it
+        }
     }
 }
 

@@ -106,6 +106,11 @@ struct KParams {
     float *out_mel, *out_a, *out_b;
     float preemph;     // != 0: pre-emphasis y[n] = x[n] - preemph x[n-1] (y[0] = x[0] - preemph x[1]) applied to the staged
                        // samples before framing (PreEmphasis.forward, models/sound.py:66-81), generic mel kernel only
+    // fused MFCC epilogue (logmel_fast_kernel<..., kDct = true> only): dct (n_mfcc, n_mels) row-major in global memory,
+    // its shared-memory copy [n_mels rounded up to even][64] at off_dct, the per-warp log-mel column float2[...] at off_col
+    const float *dct;
+    float *out_mfcc;
+    int n_mfcc, off_dct, off_col, col_bytes;
     float *out_fmask;  // nullable (B, T): SpectrogramMasker frame mask, 1 iff t * hop - win_half < clip length
     int win_half;
     long long *dbg;  // phase-timing accumulators (debug builds only)

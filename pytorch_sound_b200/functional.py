@@ -73,11 +73,42 @@ def run(plan: "_lib.Plan", wav: torch.Tensor, epi: Optional["_lib.Epilogue"], wa
         io = _lib.IO(C.sizeof(_lib.IO), spec_kind, wav.data_ptr(), B, L, wav.stride(0) if B > 1 else max(L, 1), len_ptr,
                      mel.data_ptr() if mel is not None else None, out_a.data_ptr() if out_a is not None else None,
                      out_b.data_ptr() if out_b is not None else None,
-                     frame_mask.data_ptr() if frame_mask is not None else None, int(reserve_sms), float(preemphasis))
+                     frame_mask.data_ptr() if frame_mask is not None else None, int(reserve_sms), float(preemphasis),
+                     None, None, 0, 0)
         rc = _lib.lib().b200mel_forward_io(plan.handle, C.byref(io), C.byref(epi) if epi is not None else None,
                                            C.c_void_p(stream))
     _lib.check(rc)
     return mel, out_a, out_b
+
+
+def mfcc_fused(plan: "_lib.Plan", wav: torch.Tensor, epi: "_lib.Epilogue", dct: torch.Tensor,
+               want_mel: bool = False) -> Optional[Tuple[torch.Tensor, Optional[torch.Tensor]]]:
+    """MFCC.forward (models/transforms.py:433-455) in ONE launch: the DCT applied as an epilogue of the mel kernel
+    (io.out_mfcc).  Returns (mfcc (B, n_mfcc, T), mel or None), or None when the library answers B200MEL_EUNSUP for
+    this plan / call — the caller then runs the mel launch and b200mel_mel_to_mfcc."""
+    wav = _check_wav(wav)
+    dev = wav.device
+    if dev.index != plan.device_index:
+        raise RuntimeError(f"plan lives on cuda:{plan.device_index}, wav on {dev}")
+    if dct.dim() != 2 or dct.shape[1] != plan.cfg.n_mels:
+        raise ValueError(f"dct must be (n_mfcc, {plan.cfg.n_mels}), got {tuple(dct.shape)}")
+    dct = dct.to(device=dev, dtype=torch.float32).contiguous()
+    B, L = wav.shape
+    T = plan.out_frames(L)
+    out = torch.empty((B, dct.shape[0], T), device=dev, dtype=torch.float32)
+    mel = torch.empty((B, plan.cfg.n_mels, T), device=dev, dtype=torch.float32) if want_mel else None
+    if B == 0:
+        return out, mel
+    with torch.cuda.device(dev):
+        io = _lib.IO(C.sizeof(_lib.IO), _lib.SPEC_NONE, wav.data_ptr(), B, L, wav.stride(0) if B > 1 else max(L, 1), None,
+                     mel.data_ptr() if mel is not None else None, None, None, None, 0, 0.0,
+                     dct.data_ptr(), out.data_ptr(), int(dct.shape[0]), 0)
+        rc = _lib.lib().b200mel_forward_io(plan.handle, C.byref(io), C.byref(epi),
+                                           C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    if rc == _lib.EUNSUP:
+        return None
+    _lib.check(rc)
+    return out, mel
 
 
 def _check_cuda_f32(x: torch.Tensor, what: str) -> None:

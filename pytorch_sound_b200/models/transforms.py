@@ -379,6 +379,13 @@ class MFCC(nn.Module):
     def forward(self, wav: torch.Tensor) -> torch.Tensor:
         if wav.dim() == 3 and wav.shape[1] == 1:
             wav = wav[:, 0]
+        # one launch: the DCT as an epilogue of the mel kernel, while the log-mel column is still on chip
+        # (io.out_mfcc, include/b200mel.h); geometries the fused kernel does not serve take the two launches
+        mf = self.mel_func
+        epi = _lib.make_epilogue(_lib.LOG_LN_OFFSET, 1e-6, mf.min_db, mf.max_db, False)
+        fused = functional.mfcc_fused(mf._plan(wav.device), wav, epi, self.dct_mat)
+        if fused is not None:
+            return fused[0]
         mel_spectrogram = self.mel_func(wav)
         return functional.mel_to_mfcc(mel_spectrogram, self.dct_mat)
 

@@ -59,8 +59,8 @@ def test_io_struct_matches_header(built_lib):
         decl = re.sub(r"^(const\s+)?(float|int32_t|int64_t)\s*", "", decl)
         names += [n.strip().lstrip("*").strip() for n in decl.split(",")]
     assert names == [f[0] for f in built_lib.IO._fields_]
-    # pointers / int64 are 8-byte aligned: 2 x int32, then 9 x 8 bytes, then 2 x int32
-    assert C.sizeof(built_lib.IO) == 8 + 9 * 8 + 8
+    # pointers / int64 are 8-byte aligned: 2 x int32, then 9 x 8 bytes, 2 x 4 bytes, 2 pointers, 2 x int32
+    assert C.sizeof(built_lib.IO) == 8 + 9 * 8 + 8 + 2 * 8 + 8
     lib = built_lib.lib()
     io = built_lib.IO()
     io.struct_size = 4

@@ -232,3 +232,42 @@ def test_fused_preemphasis_prologue(torch_cuda):
     xs = cuda(torch, mo.synth_clips(5, 22050, 22050, seed=9))
     v.copy_(xs)
     assert torch.equal(lm(v, preemphasis=0.97), lm(xs, preemphasis=0.97))
+
+
+def test_fused_mfcc_epilogue(torch_cuda):
+    """MFCC.forward (models/transforms.py:433-455) as ONE launch (io.out_mfcc: the DCT applied while the log-mel column
+    is on chip) against the reference's MFCC output, the float64 oracle and the two-launch path (mel kernel + DCT
+    kernel); n_mfcc 40 (two coefficient slots per lane), 13 and 64, an odd mel count; geometries the fused kernel does
+    not serve answer B200MEL_EUNSUP and the module falls back to two launches."""
+    torch = torch_cuda
+    from pytorch_sound_b200 import _lib, functional
+    from pytorch_sound_b200.models import transforms as T
+
+    extra = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_extra.npz"))
+    x = cuda(torch, extra["clips.wav"])
+    mf = T.MFCC(22050, 80, 1024, 1024, 40, 256, -50, 30, 0.0, 8000.0).cuda()
+    n0 = _lib.launch_count()
+    y = mf(x)
+    assert _lib.launch_count() == n0 + 1, "the fused epilogue is one launch"
+    assert np.abs(y.cpu().numpy() - extra["clips.mfcc"]).max() < 1e-3     # 80-term sums of log values, each within 1e-4
+    two = functional.mel_to_mfcc(mf.mel_func(x), mf.dct_mat)
+    assert float((y - two).abs().max()) < 2e-5                            # same log-mel values, different summation order
+    # mel frames and coefficients from the same launch
+    epi = _lib.make_epilogue(_lib.LOG_LN_OFFSET, 1e-6, mf.mel_func.min_db, mf.mel_func.max_db, False)
+    y2, mel = functional.mfcc_fused(mf.mel_func._plan(x.device), x, epi, mf.dct_mat, want_mel=True)
+    assert torch.equal(y2, y) and torch.equal(mel, mf.mel_func(x))
+    wav = mo.synth_clips(7, 9001, 22050, seed=4)
+    for n_mels, n_mfcc in ((80, 13), (80, 64), (79, 40), (40, 40)):
+        m = T.MFCC(22050, n_mels, 1024, 1024, n_mfcc, 256, -50, 30, 0.0, 8000.0).cuda()
+        n0 = _lib.launch_count()
+        got = m(cuda(torch, wav)).cpu().numpy()
+        ref_mel = mo.log_mel_spectrogram(wav, 22050, n_mels, 1024, 1024, 256, -50, 30, 0.0, 8000.0)
+        ref = np.einsum("km,bmt->bkt", mo.create_dct(n_mfcc, n_mels).T, ref_mel)
+        assert got.shape == ref.shape and np.abs(got - ref).max() < 1e-3, (n_mels, n_mfcc)
+    # hop 128 / a filterbank the specialised kernel has no instance for: two launches, same numbers
+    m = T.MFCC(22050, 80, 1024, 1024, 40, 128, -50, 30, 0.0, 8000.0).cuda()
+    n0 = _lib.launch_count()
+    got = m(cuda(torch, wav)).cpu().numpy()
+    assert _lib.launch_count() == n0 + 2
+    ref = np.einsum("km,bmt->bkt", mo.create_dct(40, 80).T, mo.log_mel_spectrogram(wav, 22050, 80, 1024, 1024, 128, -50, 30, 0.0, 8000.0))
+    assert np.abs(got - ref).max() < 1e-3

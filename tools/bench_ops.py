@@ -19,6 +19,11 @@ ops = {
     "STFT.transform (mag, phase)": (T.STFT(1024, 256).cuda(), lambda m, x: m.transform(x)),
     "STFTTorchAudio.forward (re, im)": (T.STFTTorchAudio(1024, 256).cuda(), lambda m, x: m(x)),
 }
+from pytorch_sound_b200 import functional as _F
+ops["MFCC.forward (DCT fused as an epilogue of the mel launch)"] = (
+    T.MFCC(22050, 80, 1024, 1024, 40, 256, -50, 30, 0.0, 8000.0).cuda(), lambda m, x: m(x))
+ops["MFCC as two launches (mel kernel + DCT kernel)"] = (
+    T.MFCC(22050, 80, 1024, 1024, 40, 256, -50, 30, 0.0, 8000.0).cuda(), lambda m, x: _F.mel_to_mfcc(m.mel_func(x), m.dct_mat))
 _mag = T.STFT(1024, 256).cuda()
 _mags = [_mag.magnitude(x) for x in xs]
 ops["LogMelScale.forward (tcgen05 mel GEMM on magnitudes in HBM)"] = (
