@@ -91,7 +91,11 @@ def kernel_name(module):
             bins = "bins < 384"
     except Exception:
         pass
-    return f"b200mel::logmel_kernel<{kind}, power 1, {bins}>, 16 warps per CTA"
+    fast = N_FFT == 1024 and HOP == 256 and os.environ.get("B200MEL_NO_FAST") is None
+    if fast and os.environ.get("B200MEL_TC") == "1" and bins == "bins < 384":
+        return "b200mel::stft_tc_kernel<power 1> (tcgen05 DFT stages, opt-in), 21 warps per CTA"
+    body = "logmel_fast_kernel (compile-time specialised geometry and mel rounds)" if fast else "logmel_kernel"
+    return f"b200mel::{body}<{kind}, power 1, {bins}>, 16 warps per CTA"
 
 
 class ClockSampler(threading.Thread):
