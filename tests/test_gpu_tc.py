@@ -138,6 +138,26 @@ def test_scales_silence_and_non_finite(tc):
     assert np.array_equal(y[1, :, 16:], ok[1, :, 16:]) and np.array_equal(y[[0, 2]], ok[[0, 2]])
 
 
+def test_misaligned_and_strided_tensors(tc):
+    """Waveform views at every 4-byte offset inside NaN guard floats, and rows with a stride: the staged copy is
+    widened to 16-byte boundaries but never leaves the tensor, and the floats the clamp drops come from global memory."""
+    torch, lib = tc
+    from pytorch_sound_b200.models import transforms as T
+
+    B, L = 5, 22050
+    x = cuda(torch, mo.synth_clips(B, L, 22050, seed=77))
+    mod = T.LogMelSpectrogram(**GEO).cuda()
+    y0 = mod(x)
+    for off in (1, 2, 3, 5):
+        buf = torch.full((B * L + 8,), float("nan"), device="cuda")
+        v = buf[off:off + B * L].view(B, L)
+        v.copy_(x)
+        assert torch.equal(mod(v), y0), off
+    wide = torch.zeros(B, L + 3, device="cuda")
+    wide[:, :L] = x
+    assert torch.equal(mod(wide[:, :L]), y0)
+
+
 def test_ineligible_plans_and_arguments_use_the_cuda_core_kernels(tc):
     """hop 128, a filterbank up to Nyquist, per-clip lengths: the launch silently stays on the CUDA-core kernels."""
     torch, lib = tc
