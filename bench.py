@@ -442,6 +442,7 @@ def main():
     #   fused_pull  kernel writes into the symmetric buffer -> b200mel_gather_pull: in-kernel barrier + 16-byte peer
     #               loads (SM kernel; the persistent extraction kernel fills the SMs, so the two serialise)
     #   fused_pull_splitR  the extraction runs on 148 - R SMs, the pull (2 R CTAs) beside it on the other R
+    #   fused_tma_splitR   the same with b200mel_gather_tma (bulk async copies through shared memory, R CTAs on R SMs)
     #   fused_copy  same buffer -> one-CTA barrier kernel + copy-engine peer copies (overlaps with the extraction)
     # The fused pipelines are captured in ONE CUDA graph (8 steps, two streams) and replayed: no host launch cost in
     # the timed region, like the `value` leg.
@@ -487,10 +488,11 @@ def main():
         a0 = rank * B_PER_GPU
         ingress = (world - 1) * B_PER_GPU * N_MELS * T * 4
         variants = [("fused_pull", "pull", 0), ("fused_copy", "copy", 1)]
-        variants += [(f"fused_pull_split{r}", "pull", r) for r in (24, 32, 48)]
+        variants += [(f"fused_pull_split{r}", "pull", r) for r in (32, 48)]
+        variants += [(f"fused_tma_split{r}", "tma", r) for r in (8, 16, 24)]
         for key, engine, spare in variants:
             try:
-                sg = SymmetricGather(engine=engine, pull_ctas=2 * spare if engine == "pull" else 0)
+                sg = SymmetricGather(engine=engine, pull_ctas=2 * spare if engine == "pull" else (spare if engine == "tma" else 0))
 
                 # spare = SMs the extraction leaves free: 1 for the barrier CTA that gates the copy engines, R for a
                 # pull kernel of 2 R CTAs running beside it, 0 when the pull uses the whole GPU after the extraction
@@ -534,6 +536,9 @@ def main():
                                               + (f"{spare} SMs beside the extraction on the other {148 - spare}" if spare
                                                  else "all SMs after the extraction"))
                                              if engine == "pull" else
+                                             (f"b200mel_gather_tma: in-kernel barrier + TMA bulk copies peer -> shared -> local, "
+                                              f"{spare} CTAs on {spare} SMs beside the extraction on the other {148 - spare}")
+                                             if engine == "tma" else
                                              "b200mel_gather_copy: one-CTA barrier kernel + copy-engine peer copies")
                                           + f"; gather of step i on a second stream under the extraction of step i+1; "
                                             f"{n_graph}-step CUDA graph replayed; no NCCL call")}

@@ -249,6 +249,13 @@ int b200mel_mel_to_mfcc(const float *mel, const float *dct, int64_t B, int32_t n
 int b200mel_gather_pull(float *local_buf, const float *const *peer_bufs, int32_t *const *peer_sync, int32_t world,
                         int32_t rank, const int64_t *block_offsets /* [world + 1] */,
                         int32_t n_ctas /* 512-thread CTAs of the pull kernel; 0 = two per SM */, void *stream);
+/* b200mel_gather_pull with the TMA engine: one thread per CTA streams the peers' blocks through a ring of
+ * shared-memory stages with bulk async copies (peer -> shared over NVLink, shared -> local), 128 KB in flight per CTA and
+ * no load / store instructions, so n_ctas = 16 (0 = 32) CTAs cover the link and the concurrent extraction kernel keeps
+ * the other SMs (io.reserve_sms = n_ctas).  Same arguments, barrier and result as b200mel_gather_pull. */
+int b200mel_gather_tma(float *local_buf, const float *const *peer_bufs, int32_t *const *peer_sync, int32_t world,
+                       int32_t rank, const int64_t *block_offsets, int32_t n_ctas, void *stream);
+
 /* SM partitioning: the extraction kernel is persistent and owns every register of the SMs it runs on, so a pull
  * kernel launched on another stream only runs beside it on SMs the extraction left free — launch the extraction
  * with b200mel_io.reserve_sms = R and the pull with n_ctas = 2 R and the two overlap (R ~ 32 of 148 SMs keeps

@@ -69,6 +69,8 @@ SYMBOLS = {
                                           C.c_void_p, C.c_void_p]),
     "b200mel_gather_pull": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_int32,
                                       C.POINTER(C.c_int64), C.c_int32, C.c_void_p]),
+    "b200mel_gather_tma": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_int32,
+                                     C.POINTER(C.c_int64), C.c_int32, C.c_void_p]),
     "b200mel_gather_copy": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_int32,
                                       C.POINTER(C.c_int64), C.c_void_p]),
     "b200mel_mel_to_mfcc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,

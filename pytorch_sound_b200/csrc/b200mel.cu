@@ -1184,12 +1184,18 @@ static GatherCtx g_gather[64];
 static std::mutex g_gather_mu;
 
 static int gather_impl(float *local_buf, const float *const *peer_bufs, int32_t *const *peer_sync, int32_t world,
-                       int32_t rank, const int64_t *block_offsets, void *stream, bool use_copy_engines, int n_ctas);
+                       int32_t rank, const int64_t *block_offsets, void *stream, bool use_copy_engines, int n_ctas,
+                       bool use_tma = false);
 
 int b200mel_gather_pull(float *local_buf, const float *const *peer_bufs, int32_t *const *peer_sync, int32_t world,
                         int32_t rank, const int64_t *block_offsets, int32_t n_ctas, void *stream) {
     if (n_ctas < 0) return fail(B200MEL_EINVAL, "gather_pull: negative n_ctas");
     return gather_impl(local_buf, peer_bufs, peer_sync, world, rank, block_offsets, stream, false, n_ctas);
+}
+int b200mel_gather_tma(float *local_buf, const float *const *peer_bufs, int32_t *const *peer_sync, int32_t world,
+                       int32_t rank, const int64_t *block_offsets, int32_t n_ctas, void *stream) {
+    if (n_ctas < 0) return fail(B200MEL_EINVAL, "gather_tma: negative n_ctas");
+    return gather_impl(local_buf, peer_bufs, peer_sync, world, rank, block_offsets, stream, false, n_ctas, true);
 }
 int b200mel_gather_copy(float *local_buf, const float *const *peer_bufs, int32_t *const *peer_sync, int32_t world,
                         int32_t rank, const int64_t *block_offsets, void *stream) {
@@ -1198,7 +1204,8 @@ int b200mel_gather_copy(float *local_buf, const float *const *peer_bufs, int32_t
 }
 
 static int gather_impl(float *local_buf, const float *const *peer_bufs, int32_t *const *peer_sync, int32_t world,
-                       int32_t rank, const int64_t *block_offsets, void *stream, bool use_copy_engines, int n_ctas) {
+                       int32_t rank, const int64_t *block_offsets, void *stream, bool use_copy_engines, int n_ctas,
+                       bool use_tma) {
     if (!local_buf || !peer_bufs || !block_offsets) return fail(B200MEL_EINVAL, "gather_pull: null pointer");
     if (world < 1 || world > 16 || rank < 0 || rank >= world) return fail(B200MEL_EINVAL, "gather_pull: need 1 <= world <= 16, 0 <= rank < world");
     PullArgs a;
@@ -1219,7 +1226,11 @@ static int gather_impl(float *local_buf, const float *const *peer_bufs, int32_t 
     if (int rc = current_sms(&sms)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     a.pull = use_copy_engines ? 0 : 1;
-    gather_pull_kernel<<<use_copy_engines ? 1 : (n_ctas > 0 ? n_ctas : sms * 2), 512, 0, st>>>(local_buf, a);
+    if (use_tma) {
+        cudaFuncSetAttribute(gather_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPullStages * kPullChunk);  // per device
+        gather_tma_kernel<<<n_ctas > 0 ? n_ctas : 32, 128, kPullStages * kPullChunk, st>>>(local_buf, a);
+    } else
+        gather_pull_kernel<<<use_copy_engines ? 1 : (n_ctas > 0 ? n_ctas : sms * 2), 512, 0, st>>>(local_buf, a);
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "gather launch");

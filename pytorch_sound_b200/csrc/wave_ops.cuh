@@ -230,6 +230,128 @@ __global__ void __launch_bounds__(512, 2) gather_pull_kernel(float *__restrict__
     }
 }
 
+// The same gather with the TMA engine instead of the load / store units: one thread per CTA streams the peers' blocks
+// through a ring of shared-memory stages with bulk async copies — cp.async.bulk global (peer, over NVLink) -> shared,
+// completion on an mbarrier, then cp.async.bulk shared -> global (local buffer) — kPullStages x kPullChunk bytes in
+// flight per CTA with no registers and no load instructions involved, so a handful of CTAs covers the NVLink
+// bandwidth-delay product (~770 GB/s x ~3 us = 2.3 MB) and the SMs the gather takes away from the concurrent
+// extraction kernel shrink from 48 to 16.  Consecutive chunks of a CTA go to different peers (every link busy all
+// the time).  Barrier, epoch and the unaligned heads / tails of a block are those of gather_pull_kernel.
+constexpr int kPullStages = 4, kPullChunk = 32768;
+__global__ void __launch_bounds__(128, 1) gather_tma_kernel(float *__restrict__ local, const PullArgs a) {
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ uint64_t s_full[kPullStages];
+    __shared__ int s_step;
+    int *sync = a.peer_sync[a.rank];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kPullStages; ++i) mbar_init(smem_u32(s_full + i), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (sync) {
+        if (threadIdx.x == 0) s_step = *reinterpret_cast<volatile int *>(sync + a.world) + 1;
+        __syncthreads();
+        const int step = s_step;
+        const int r = threadIdx.x;
+        if (r < a.world && r != a.rank) {
+            if (blockIdx.x == 0) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(a.peer_sync[r] + a.rank), "r"(step) : "memory");
+            int seen;
+            unsigned spins = 0;
+            do {
+                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(sync + r) : "memory");
+                if (seen - step < 0 && ++spins > (1u << 26)) __trap();  // a peer never arrived: CUDA error, not a hung GPU
+            } while (seen - step < 0);
+        }
+    }
+    __syncthreads();
+    auto body = [&](int r, long long &lo4, long long &bytes) {  // 16-byte aligned body of block r: first float, bytes
+        const long long lo = a.off[r], hi = a.off[r + 1];
+        long long b_lo = (lo + 3) & ~3LL, b_hi = hi & ~3LL;
+        if (b_lo >= b_hi) b_lo = b_hi = hi;
+        lo4 = b_lo;
+        bytes = (b_hi - b_lo) * 4;
+    };
+    // unaligned heads / tails (<= 3 floats each side of a block): scalar, by the threads of CTA 0
+    if (blockIdx.x == 0) {
+        for (int r = 0; r < a.world; ++r) {
+            if (r == a.rank) continue;
+            const long long lo = a.off[r], hi = a.off[r + 1];
+            long long lo4, bytes;
+            body(r, lo4, bytes);
+            const float *src = a.peer[r];
+            for (long long e = lo + threadIdx.x; e < min(lo4, hi); e += blockDim.x) local[e] = *reinterpret_cast<const volatile float *>(src + e);
+            for (long long e = lo4 + bytes / 4 + threadIdx.x; e < hi; e += blockDim.x) local[e] = *reinterpret_cast<const volatile float *>(src + e);
+        }
+    }
+    if (threadIdx.x == 0) {
+        // chunk id = c * (world - 1) + p: chunk c of the p-th peer after this rank; ids blockIdx, blockIdx + gridDim, ...
+        const int peers = a.world - 1;
+        long long max_chunks = 0;
+        for (int r = 0; r < a.world; ++r) {
+            long long lo4, bytes;
+            body(r, lo4, bytes);
+            if (r != a.rank) max_chunks = max(max_chunks, (bytes + kPullChunk - 1) / kPullChunk);
+        }
+        const long long n_ids = max_chunks * peers;
+        struct Chunk { const unsigned char *src; unsigned char *dst; uint32_t bytes; };
+        auto chunk_of = [&](long long id, Chunk &ck) -> bool {  // false: this id is past the end of its (shorter) block
+            const long long c = id / peers;
+            const int r = (a.rank + 1 + (int)(id - c * peers)) % a.world;
+            long long lo4, bytes;
+            body(r, lo4, bytes);
+            const long long off = c * kPullChunk;
+            if (off >= bytes) return false;
+            ck.src = reinterpret_cast<const unsigned char *>(a.peer[r] + lo4) + off;
+            ck.dst = reinterpret_cast<unsigned char *>(local + lo4) + off;
+            ck.bytes = (uint32_t)min((long long)kPullChunk, bytes - off);
+            return true;
+        };
+        long long next_load = blockIdx.x;   // next chunk id to request
+        long long loaded = 0, stored = 0;   // chunks requested / written so far (ring positions)
+        Chunk pending[kPullStages];
+        auto request = [&]() {              // issue the load of the next valid chunk into ring stage loaded % kPullStages
+            Chunk ck;
+            while (next_load < n_ids && !chunk_of(next_load, ck)) next_load += gridDim.x;
+            if (next_load >= n_ids) return false;
+            next_load += gridDim.x;
+            const int st = (int)(loaded % kPullStages);
+            const uint32_t bar = smem_u32(s_full + st);
+            pending[st] = ck;
+            mbar_arrive_expect_tx(bar, ck.bytes);
+            tma_load_1d(smem_u32(ring + st * kPullChunk), ck.src, ck.bytes, bar);
+            ++loaded;
+            return true;
+        };
+        for (int i = 0; i < kPullStages; ++i)
+            if (!request()) break;
+        while (stored < loaded) {
+            const int st = (int)(stored % kPullStages);
+            mbar_wait(smem_u32(s_full + st), (uint32_t)(stored / kPullStages) & 1u);
+            const Chunk ck = pending[st];
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(ck.dst)),
+                         "r"(smem_u32(ring + st * kPullChunk)), "r"(ck.bytes)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            ++stored;
+            // the stage may be refilled once the store has READ it; the other stages' loads stay in flight meanwhile
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            request();
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every store has landed before the epoch moves on
+    }
+    if (sync) {  // the last CTA of the launch advances the epoch
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const int t = atomicAdd(sync + a.world + 1, 1);
+            if (t == (int)gridDim.x - 1) {
+                sync[a.world + 1] = 0;
+                __threadfence();
+                *reinterpret_cast<volatile int *>(sync + a.world) = s_step;
+            }
+        }
+    }
+}
+
 // mel (B, M, T) -> mfcc (B, C, T), DCT matrix in CONSTANT memory.  A thread owns one (b, t) column: its M mel values
 // are read once into registers (a warp reads 32 consecutive frames of a mel row: full 128-byte lines) and every
 // output row is M FFMAs whose weight operand comes straight from the constant bank — warp-uniform, so it costs no

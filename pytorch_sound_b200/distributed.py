@@ -75,14 +75,16 @@ class SymmetricGather:
     N_SLOTS = 3
 
     def __init__(self, group=None, engine: str = "pull", pull_ctas: int = 0):
-        """engine="pull": SM kernel with 16-byte peer loads (fastest; to overlap it with an extraction on another stream,
+        """engine="pull": SM kernel with 16-byte peer loads (to overlap it with an extraction on another stream,
         launch that extraction with reserve_sms=R and give the pull pull_ctas=2 R);
+        engine="tma": the same gather driven by the TMA engine (bulk async copies through shared memory, one CTA per
+        SM; beside an extraction with reserve_sms=R give it pull_ctas=R — 16 are enough);
         engine="copy": one-CTA barrier kernel + copy-engine transfers (overlaps with an extraction kernel that fills
         the SMs on another stream)."""
         import torch.distributed._symmetric_memory as symm_mem
 
-        if engine not in ("pull", "copy"):
-            raise ValueError("engine must be 'pull' or 'copy'")
+        if engine not in ("pull", "tma", "copy"):
+            raise ValueError("engine must be 'pull', 'tma' or 'copy'")
         self.engine = engine
         self.pull_ctas = int(pull_ctas)  # CTAs of the pull kernel (0 = two per SM); 2 R beside an extraction with reserve_sms=R
 
@@ -145,6 +147,9 @@ class SymmetricGather:
             if self.engine == "pull":
                 rc = _lib.lib().b200mel_gather_pull(buf.data_ptr(), args[0], args[1], self.world, self.rank, args[2],
                                                     self.pull_ctas, st)
+            elif self.engine == "tma":
+                rc = _lib.lib().b200mel_gather_tma(buf.data_ptr(), args[0], args[1], self.world, self.rank, args[2],
+                                                   self.pull_ctas, st)
             else:
                 rc = _lib.lib().b200mel_gather_copy(buf.data_ptr(), args[0], args[1], self.world, self.rank, args[2], st)
         _lib.check(rc)

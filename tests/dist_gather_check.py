@@ -33,8 +33,11 @@ def main():
     for n_clips, L in [(64, 22050), (8 * world, 5000), (8 * world + 3, 7001), (world + 1, 2000)]:
         x = torch.from_numpy(mo.synth_clips(n_clips, L, 22050, seed=99 + n_clips)).to(dev)
         single = lm(x)                                   # the whole batch on this GPU
-        for mode in ("nccl", "fused"):
-            ext = ShardedExtractor(lm, mode=mode)
+        for mode in ("nccl", "fused", "fused-tma"):
+            ext = ShardedExtractor(lm, mode=mode.split("-")[0])
+            if mode == "fused-tma":   # the same fused gather driven by the TMA engine (b200mel_gather_tma)
+                from pytorch_sound_b200.distributed import SymmetricGather
+                ext._sg = SymmetricGather(engine="tma", pull_ctas=8)
             for rep in range(2):                         # twice: buffers / barriers are reused across steps
                 got = ext(x)
                 a, b = shard_range(n_clips, rank, world)
