@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200MEL_VERSION 200 /* 0.2.0 */
+#define B200MEL_VERSION 210 /* 0.2.1: b200mel_io gained dct_mat / out_mfcc / n_mfcc (struct_size 112), b200mel_gather_tma */
 
 /* error codes */
 #define B200MEL_OK 0
