@@ -407,15 +407,17 @@ static int upload_filterbank(b200mel_plan *pl, const float *W_log, int n_mels, i
 typedef void (*kernel_fn)(const KParams);
 // Mel kernels: {pair, split} x {magnitude, power} x {all bins, bins < 384 (pair only)}, 16 warps per CTA; the
 // spectrum-output operators use the 8-warp cooperative kernel of spec_kernel.cuh.
-template <int kTop>
+template <int kTop, bool kPre>
 static kernel_fn pick_mel_kernel(bool pair, int power) {
-    if (pair) return power == 2 ? logmel_kernel<true, 2, kTop> : logmel_kernel<true, 1, kTop>;
-    return power == 2 ? logmel_kernel<false, 2, 16> : logmel_kernel<false, 1, 16>;
+    if (pair) return power == 2 ? logmel_kernel<true, 2, kTop, kPre> : logmel_kernel<true, 1, kTop, kPre>;
+    return power == 2 ? logmel_kernel<false, 2, 16, kPre> : logmel_kernel<false, 1, 16, kPre>;
 }
-static kernel_fn pick_kernel(bool pair, int spec, bool mel, int power, int top_groups) {
-    if (mel) return top_groups == 12 ? pick_mel_kernel<12>(pair, power) : pick_mel_kernel<16>(pair, power);
+// pre: the instantiation with the fused pre-emphasis prologue (io.preemphasis != 0)
+static kernel_fn pick_kernel(bool pair, int spec, bool mel, int power, int top_groups, bool pre = false) {
     (void)spec;
-    return nullptr;
+    if (!mel) return nullptr;
+    if (pre) return top_groups == 12 ? pick_mel_kernel<12, true>(pair, power) : pick_mel_kernel<16, true>(pair, power);
+    return top_groups == 12 ? pick_mel_kernel<12, false>(pair, power) : pick_mel_kernel<16, false>(pair, power);
 }
 template <bool kPair, int kSpec>
 static kernel_fn pick_spec_shape(int groups) {
@@ -676,7 +678,8 @@ int b200mel_plan_create(const b200mel_config *cfg, b200mel_plan **out) {
             break;
         for (int power = 1; power <= 2 && e == cudaSuccess; ++power)
             for (int top = 12; top <= 16 && e == cudaSuccess; top += 4)
-                e = cudaFuncSetAttribute(pick_kernel(pl->pair, 0, true, power, top), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+                for (int pre = 0; pre <= 1 && e == cudaSuccess; ++pre)
+                    e = cudaFuncSetAttribute(pick_kernel(pl->pair, 0, true, power, top, pre != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         for (int spec = 1; spec <= 3 && e == cudaSuccess; ++spec)
         {
             e = cudaFuncSetAttribute(pick_spec_kernel(pl->pair, spec, pl->sp[spec].groups),
@@ -787,6 +790,8 @@ int b200mel_forward_io(const b200mel_plan *pl, const b200mel_io *io, const b200m
     frames_host(pl, L, &T);
     if (T <= 0) return fail(B200MEL_EINVAL, "forward: clip shorter than one frame");
     if (T > 0x7fffffff) return fail(B200MEL_EINVAL, "forward: too many frames");
+    if (out_mel && (int64_t)pl->cfg.n_mels * T > 0x7fffffff)
+        return fail(B200MEL_EINVAL, "forward: n_mels * frames per clip exceeds 2^31 - 1 (the kernels index a clip's mel block with 32 bits)");
 
     KParams p;
     memset(&p, 0, sizeof(p));
@@ -918,7 +923,7 @@ int b200mel_forward_io(const b200mel_plan *pl, const b200mel_io *io, const b200m
         cfg.gridDim = dim3((unsigned)n_cta);
         cfg.blockDim = dim3(pl->n_warps * 32);
         kernel_fn fn = (!lengths && p.use_log && !p.out_fmask && p.preemph == 0.f) ? pick_fast_kernel(pl) : nullptr;
-        if (!fn) fn = pick_kernel(pl->pair, 0, true, pl->cfg.power, pl->top_groups);
+        if (!fn) fn = pick_kernel(pl->pair, 0, true, pl->cfg.power, pl->top_groups, p.preemph != 0.f);
         le = cudaLaunchKernelEx(&cfg, fn, p);
         g_launches.fetch_add(1);
     }

@@ -448,13 +448,16 @@ __device__ __forceinline__ Desc request_task(const KParams &p, int b, int q, int
     return d;
 }
 
+template <bool kPre>
 __device__ __forceinline__ void patch_halo_smem(const KParams &p, const Desc &d, float *stage, int lane) {
     const int s_first = d.t0 * p.hop - p.pad;
     const int span = p.n_fft + ((d.flags & 2u) ? p.hop : 0);
     const CopyGeom g = copy_geom(p, d.b, s_first, span, d.Li);
-    if (p.preemph != 0.f && g.c_hi > g.c_lo)  // warp-uniform
-        preemphasize_stage(p.wav + (long long)d.b * p.row_stride, stage + g.delta - s_first, g.c_lo, g.c_hi, p.preemph, lane);
-    if (g.patch) patch_stage(p, d.b, s_first, span, d.Li, g, stage, lane, p.preemph);
+    if constexpr (kPre) {
+        if (g.c_hi > g.c_lo)  // warp-uniform
+            preemphasize_stage(p.wav + (long long)d.b * p.row_stride, stage + g.delta - s_first, g.c_lo, g.c_hi, p.preemph, lane);
+    }
+    if (g.patch) patch_stage(p, d.b, s_first, span, d.Li, g, stage, lane, kPre ? p.preemph : 0.f);
 }
 
 // Pair mode, stage -> registers with the window applied: a[j] = {x_t[32 j + lane], x_t+1[32 j + lane]} * w[32 j + lane].
@@ -507,7 +510,9 @@ __device__ __forceinline__ void load_windowed_pair(float2 *a, const float *x0, c
 // kPower: 1 magnitude, 2 power.  kTop: 32-bin groups of the spectrum that are separated in pair mode — 16 = all
 // 513 bins, 12 = bins 0..383 only (plans whose filterbank ends below bin 384, e.g. fmax 8000 Hz at 22050 Hz; the
 // unused FFT outputs are dead code for the compiler).  16 warps per CTA (128 registers per thread).
-template <bool kPair, int kPower, int kTop>
+// kPre: the fused pre-emphasis prologue (io.preemphasis != 0) is a separate instantiation — as a run-time branch of the
+// one body it cost the split-mode kernel 72 bytes of spills and 10 % of its speed at C4 (55 us instead of 49 us).
+template <bool kPair, int kPower, int kTop, bool kPre = false>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -618,7 +623,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
     }
 #endif
 
-    auto patch_halo = [&](const Desc &d) { patch_halo_smem(p, d, stage, lane); };
+    auto patch_halo = [&](const Desc &d) { patch_halo_smem<kPre>(p, d, stage, lane); };
 
     for (; task < p.n_tasks; task += stride) {
         const Desc d = cur;
@@ -636,7 +641,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
             // -------------------------------------------------------------- stage -> registers, windowed
             mbar_wait(bar, parity);
             parity ^= 1;
-            if ((d.flags & 4u) || p.preemph != 0.f) patch_halo(d);
+            if ((d.flags & 4u) || kPre) patch_halo(d);
             const float *x0 = stage + d.delta + lane;
             PHASE_MARK(2);  // wait for the TMA stage
             if constexpr (kPair) {
@@ -760,7 +765,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_kernel(const KParams
                 const float y0 = epilogue(acc0, p), y1 = epilogue(acc1, p);
                 PHASE_MARK(11);  // log epilogue
                 if (ce.y >= 0) {
-                    float *o = orow + (long long)ce.y * p.T;
+                    float *o = orow + ce.y * p.T;  // n_mels * T < 2^31 is checked by the host (a 64-bit product here spills in split mode)
                     o[0] = y0;
                     if (kPair && valid1) o[1] = y1;
                 }

@@ -26,7 +26,7 @@ from pytorch_sound_b200 import _lib
 _lib.LIB_PATH = %(lib)r
 from pytorch_sound_b200.models.transforms import LogMelSpectrogram
 B, L = %(B)d, %(L)d
-m = LogMelSpectrogram(22050, 80, 1024, 1024, 256, -50, 30, 0., 8000.).cuda()
+m = LogMelSpectrogram(*%(geo)r).cuda()
 g0 = torch.Generator(device="cuda").manual_seed(1)
 n = %(n)d
 xs = [torch.randn(B, L, device="cuda", generator=g0) * 0.1 for _ in range(n)]
@@ -70,7 +70,10 @@ def build_variants(specs):
 
 def run_variants(workload):
     import torch
-    B, L, n = {"C2": (256, 22050, 8), "C3": (256, 88200, 3)}[workload]
+    B, L, n, geo = {"C2": (256, 22050, 8, (22050, 80, 1024, 1024, 256, -50, 30, 0., 8000.)),
+                    "C3": (256, 88200, 3, (22050, 80, 1024, 1024, 256, -50, 30, 0., 8000.)),
+                    "C4": (16, 441000, 8, (44100, 128, 2048, 2048, 512, -50, 30, 0., None)),
+                    "C5": (8192, 8000, 2, (16000, 80, 1024, 1024, 256, -50, 30, 0., 8000.))}[workload]
     ref = None
     libs = [os.path.join(PKG, "libb200mel.so")] + sorted(glob.glob(os.path.join(VAR, "var_*.so")))
     for lib in libs:
@@ -80,7 +83,7 @@ def run_variants(workload):
         env = dict(os.environ)
         env.update(meta["env"])
         out = os.path.join(ROOT, "gpurun_out", "var_out.pt")
-        r = subprocess.run([sys.executable, "-c", CHILD % dict(root=ROOT, lib=lib, out=out, B=B, L=L, n=n)],
+        r = subprocess.run([sys.executable, "-c", CHILD % dict(root=ROOT, lib=lib, out=out, B=B, L=L, n=n, geo=geo)],
                            capture_output=True, text=True, env=env)
         tag = os.path.basename(lib)
         if r.returncode:
