@@ -138,6 +138,25 @@ def test_scales_silence_and_non_finite(tc):
     assert np.array_equal(y[1, :, 16:], ok[1, :, 16:]) and np.array_equal(y[[0, 2]], ok[[0, 2]])
 
 
+def test_power_spectrogram_variant_and_norm_epilogue(tc):
+    """LogMelSpectrogramTorchAudio (power 2, HTK scale, no area norm) with a filterbank below bin 384, and the fused
+    norm_mel epilogue, through the tensor-core kernel."""
+    torch, lib = tc
+    from pytorch_sound_b200.models import transforms as T
+
+    wav = mo.synth_clips(6, 12000, 22050, seed=21)
+    x = cuda(torch, wav)
+    n0 = lib.b200mel_debug_tc_launch_count()
+    y = T.LogMelSpectrogramTorchAudio(22050, 64, 1024, 1024, 256, -50, 30, 0.0, 8000.0).cuda()(x)
+    ref = mo.log_mel_spectrogram_torchaudio(wav.astype(np.float64), 22050, 64, 1024, 1024, 256, -50, 30, 0.0, 8000.0)
+    assert mo.parity_error(y.cpu().numpy(), ref) < TOL
+    lm = T.LogMelSpectrogram(22050, 80, 1024, 1024, 256, -50, 30, 0.0, 8000.0).cuda()
+    yn = lm(x, norm=True)
+    refn = mo.norm_mel(mo.log_mel_spectrogram(wav.astype(np.float64), min_db=-50, max_db=30, **GEO))
+    assert mo.parity_error(yn.cpu().numpy(), refn) < TOL
+    assert lib.b200mel_debug_tc_launch_count() == n0 + 2
+
+
 def test_misaligned_and_strided_tensors(tc):
     """Waveform views at every 4-byte offset inside NaN guard floats, and rows with a stride: the staged copy is
     widened to 16-byte boundaries but never leaves the tensor, and the floats the clamp drops come from global memory."""
