@@ -33,8 +33,15 @@ class GpuFeatureLoader:
     zero padding would (reflect at the clip's own end, zero frames beyond it)."""
 
     def __init__(self, loader: Iterable, features: Sequence[Tuple[int, Callable]], device: Optional[str] = None,
-                 mask_index: Optional[int] = None):
+                 mask_index: Optional[int] = None, prefetch: bool = False):
+        """`prefetch=True`: the host->device copies and the feature kernels of batch i + 1 are enqueued on a side
+        stream while the consumer still works on batch i on its own stream (the batch is handed over with an event
+        wait, its tensors are marked with `record_stream`), so with a pinned-memory loader (`pin_memory=True`,
+        data/dataset.py:180) the PCIe transfer — which bounds the end-to-end rate, DESIGN.md section 6 — overlaps
+        the training step instead of preceding it."""
         self.loader = loader
+        self.prefetch = bool(prefetch)
+        self._side = None
         self.features = list(features)
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         self.mask_index = mask_index
@@ -65,5 +72,35 @@ class GpuFeatureLoader:
         return batch + feats
 
     def __iter__(self):
+        if not self.prefetch:
+            for batch in self.loader:
+                yield self.attach(batch)
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        side = self._side
+
+        def stage(batch):
+            side.wait_stream(torch.cuda.current_stream(self.device))  # buffers the consumer freed may be reused here
+            with torch.cuda.stream(side):
+                out = self.attach(batch)
+                ready = torch.cuda.Event()
+                ready.record(side)
+            return out, ready
+
+        pending = None
         for batch in self.loader:
-            yield self.attach(batch)
+            nxt = stage(batch)
+            if pending is not None:
+                yield self._hand_over(*pending)
+            pending = nxt
+        if pending is not None:
+            yield self._hand_over(*pending)
+
+    def _hand_over(self, batch, ready):
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ready)
+        for x in batch:
+            if isinstance(x, torch.Tensor) and x.is_cuda:
+                x.record_stream(cur)  # allocated on the side stream, used (and later freed) on the consumer's
+        return batch

@@ -271,3 +271,35 @@ def test_fused_mfcc_epilogue(torch_cuda):
     assert _lib.launch_count() == n0 + 2
     ref = np.einsum("km,bmt->bkt", mo.create_dct(40, 80).T, mo.log_mel_spectrogram(wav, 22050, 80, 1024, 1024, 128, -50, 30, 0.0, 8000.0))
     assert np.abs(got - ref).max() < 1e-3
+
+
+def test_feature_loader_prefetch(torch_cuda):
+    """GpuFeatureLoader(prefetch=True): batch i + 1 is copied and extracted on a side stream while the consumer works on
+    batch i — same batches, same order, bit-equal features, also when the consumer keeps its stream busy and when
+    it runs on a non-default stream."""
+    torch = torch_cuda
+    from pytorch_sound_b200.data.feature_loader import GpuFeatureLoader
+    from pytorch_sound_b200.models import transforms as T
+
+    lm = T.LogMelSpectrogram(**GEO)
+    rng = np.random.default_rng(3)
+    batches = []
+    for i in range(7):
+        n = 3000 + 500 * i
+        wav = torch.from_numpy((0.1 * rng.standard_normal((4 + i, n))).astype(np.float32)).pin_memory()
+        mask = torch.ones(4 + i, n).pin_memory()
+        mask[0, n // 2:] = 0
+        batches.append([wav, mask])
+    plain = [[t.clone() for t in b] for b in GpuFeatureLoader(batches, [(0, lm)], mask_index=-1)]
+    burn = torch.randn(2048, 2048, device="cuda")
+    for stream in (torch.cuda.current_stream(), torch.cuda.Stream()):
+        with torch.cuda.stream(stream):
+            got = []
+            for b in GpuFeatureLoader(batches, [(0, lm)], mask_index=-1, prefetch=True):
+                burn = burn @ burn * 1e-3          # the consumer's own work on its stream
+                got.append([t.clone() for t in b])
+        torch.cuda.synchronize()
+        assert len(got) == len(plain)
+        for a, b in zip(got, plain):
+            assert len(a) == len(b) == 3
+            assert all(torch.equal(x, y) for x, y in zip(a, b))
