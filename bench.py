@@ -490,6 +490,9 @@ def main():
         variants = [("fused_pull", "pull", 0), ("fused_copy", "copy", 1)]
         variants += [(f"fused_pull_split{r}", "pull", r) for r in (32, 48)]
         variants += [(f"fused_tma_split{r}", "tma", r) for r in (8, 16, 24)]
+        only = os.environ.get("B200MEL_BENCH_GATHER")   # e.g. "tma:16,24,32,40": just these TMA splits (A/B runs)
+        if only and only.startswith("tma:"):
+            variants = [(f"fused_tma_split{int(r)}", "tma", int(r)) for r in only[4:].split(",")]
         for key, engine, spare in variants:
             try:
                 sg = SymmetricGather(engine=engine, pull_ctas=2 * spare if engine == "pull" else (spare if engine == "tma" else 0))

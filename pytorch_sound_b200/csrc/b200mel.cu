@@ -1232,8 +1232,14 @@ static int gather_impl(float *local_buf, const float *const *peer_bufs, int32_t 
     cudaStream_t st = (cudaStream_t)stream;
     a.pull = use_copy_engines ? 0 : 1;
     if (use_tma) {
-        cudaFuncSetAttribute(gather_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPullStages * kPullChunk);  // per device
-        gather_tma_kernel<<<n_ctas > 0 ? n_ctas : 32, 128, kPullStages * kPullChunk, st>>>(local_buf, a);
+        static const int stages = [] {   // B200MEL_PULL_STAGES: ring depth of the TMA pull (A/B measurements), default 4
+            const char *e = getenv("B200MEL_PULL_STAGES");
+            const int v = e ? atoi(e) : kPullStages;
+            return v < 2 ? 2 : (v > kPullMaxStages ? kPullMaxStages : v);
+        }();
+        a.stages = stages;
+        cudaFuncSetAttribute(gather_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPullMaxStages * kPullChunk);  // per device
+        gather_tma_kernel<<<n_ctas > 0 ? n_ctas : 32, 128, stages * kPullChunk, st>>>(local_buf, a);
     } else
         gather_pull_kernel<<<use_copy_engines ? 1 : (n_ctas > 0 ? n_ctas : sms * 2), 512, 0, st>>>(local_buf, a);
     g_launches.fetch_add(1);

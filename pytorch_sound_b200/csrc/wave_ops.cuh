@@ -137,6 +137,7 @@ struct PullArgs {
                                 // [world + 1] ticket; null = the caller orders the ranks itself
     int world, rank;
     int pull;                   // 0: barrier only (the copies are done by the copy engines, b200mel_gather_copy)
+    int stages;                 // gather_tma_kernel: ring stages in use (<= kPullMaxStages)
 };
 // The cross-rank barrier lives INSIDE the kernel (no separate barrier launch, CUDA-graph replayable): the step
 // number is epoch + 1, where the epoch word is advanced by the last CTA of every launch — so it is the same for
@@ -237,14 +238,15 @@ __global__ void __launch_bounds__(512, 2) gather_pull_kernel(float *__restrict__
 // bandwidth-delay product (~770 GB/s x ~3 us = 2.3 MB) and the SMs the gather takes away from the concurrent
 // extraction kernel shrink from 48 to 16.  Consecutive chunks of a CTA go to different peers (every link busy all
 // the time).  Barrier, epoch and the unaligned heads / tails of a block are those of gather_pull_kernel.
-constexpr int kPullStages = 4, kPullChunk = 32768;
+constexpr int kPullStages = 4, kPullMaxStages = 7, kPullChunk = 32768;   // default / largest ring (7 x 32 KB = 224 KB)
 __global__ void __launch_bounds__(128, 1) gather_tma_kernel(float *__restrict__ local, const PullArgs a) {
     extern __shared__ __align__(128) unsigned char ring[];
-    __shared__ uint64_t s_full[kPullStages];
+    __shared__ uint64_t s_full[kPullMaxStages];
     __shared__ int s_step;
     int *sync = a.peer_sync[a.rank];
+    const int n_stages = a.stages;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kPullStages; ++i) mbar_init(smem_u32(s_full + i), 1);
+        for (int i = 0; i < n_stages; ++i) mbar_init(smem_u32(s_full + i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (sync) {
@@ -307,13 +309,13 @@ __global__ void __launch_bounds__(128, 1) gather_tma_kernel(float *__restrict__ 
         };
         long long next_load = blockIdx.x;   // next chunk id to request
         long long loaded = 0, stored = 0;   // chunks requested / written so far (ring positions)
-        Chunk pending[kPullStages];
+        Chunk pending[kPullMaxStages];
         auto request = [&]() {              // issue the load of the next valid chunk into ring stage loaded % kPullStages
             Chunk ck;
             while (next_load < n_ids && !chunk_of(next_load, ck)) next_load += gridDim.x;
             if (next_load >= n_ids) return false;
             next_load += gridDim.x;
-            const int st = (int)(loaded % kPullStages);
+            const int st = (int)(loaded % n_stages);
             const uint32_t bar = smem_u32(s_full + st);
             pending[st] = ck;
             mbar_arrive_expect_tx(bar, ck.bytes);
@@ -321,11 +323,11 @@ __global__ void __launch_bounds__(128, 1) gather_tma_kernel(float *__restrict__ 
             ++loaded;
             return true;
         };
-        for (int i = 0; i < kPullStages; ++i)
+        for (int i = 0; i < n_stages; ++i)
             if (!request()) break;
         while (stored < loaded) {
-            const int st = (int)(stored % kPullStages);
-            mbar_wait(smem_u32(s_full + st), (uint32_t)(stored / kPullStages) & 1u);
+            const int st = (int)(stored % n_stages);
+            mbar_wait(smem_u32(s_full + st), (uint32_t)(stored / n_stages) & 1u);
             const Chunk ck = pending[st];
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(ck.dst)),
                          "r"(smem_u32(ring + st * kPullChunk)), "r"(ck.bytes)
