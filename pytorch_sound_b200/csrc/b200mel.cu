@@ -450,8 +450,9 @@ static kernel_fn pick_spec_kernel(bool pair, int spec, int groups) {
 
 // Fast-path instantiations (logmel_fast.cuh): {bins < 384, all bins} x round signatures of the filterbanks the
 // reference's defaults and the BASELINE configs produce.  A plan whose signature is not listed uses the generic kernel.
-struct FastEntry { int top; unsigned sig; int power; kernel_fn fn, fn_dct; };
-#define B200MEL_FAST(top, sig) {top, sig, 1, logmel_fast_kernel<top, sig, 1>, logmel_fast_kernel<top, sig, 1, true>}
+struct FastEntry { int top; unsigned sig; int power; kernel_fn fn, fn_dct, fn_len; };
+#define B200MEL_FAST(top, sig) \
+    {top, sig, 1, logmel_fast_kernel<top, sig, 1>, logmel_fast_kernel<top, sig, 1, true>, logmel_fast_kernel<top, sig, 1, false, true>}
 static const FastEntry g_fast[] = {
     B200MEL_FAST(12, 0x731u),  // 22050 Hz / 1024 / 80 mels / 0-8000 Hz: settings.py, C2, C3, HiFi-GAN front-end
     B200MEL_FAST(16, 0xa32u),  // 16000 Hz / 1024 / 80 mels / 0-8000 Hz: C5
@@ -468,13 +469,13 @@ static unsigned plan_signature(const b200mel_plan *pl) {
     return sig;
 }
 static const bool g_no_fast = getenv("B200MEL_NO_FAST") != nullptr;  // A/B: always run the generic kernel
-static kernel_fn pick_fast_kernel(const b200mel_plan *pl, bool dct = false) {
+static kernel_fn pick_fast_kernel(const b200mel_plan *pl, bool dct = false, bool len = false) {
     if ((g_no_fast && !dct) || !pl->pair || pl->pair_frames != 2 || pl->cfg.hop_length != kFastHop || pl->cfg.win_length != pl->phys_n_fft ||
         pl->cfg.n_mels <= 0 || g_table_window || pl->n_warps != kMaxWarps)
         return nullptr;
     const unsigned sig = plan_signature(pl);
     for (const FastEntry &e : g_fast)
-        if (e.top == pl->top_groups && e.sig == sig && e.power == pl->cfg.power) return dct ? e.fn_dct : e.fn;
+        if (e.top == pl->top_groups && e.sig == sig && e.power == pl->cfg.power) return dct ? e.fn_dct : (len ? e.fn_len : e.fn);
     return nullptr;
 }
 
@@ -690,6 +691,7 @@ int b200mel_plan_create(const b200mel_config *cfg, b200mel_plan **out) {
         for (const FastEntry &fe : g_fast) {
             if (e == cudaSuccess) e = cudaFuncSetAttribute(fe.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(fe.fn_dct, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(fe.fn_len, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         }
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaFuncSetAttribute (is the library built for this GPU?)"); break; }
     } while (0);
@@ -922,7 +924,7 @@ int b200mel_forward_io(const b200mel_plan *pl, const b200mel_io *io, const b200m
     } else if (out_mel) {
         cfg.gridDim = dim3((unsigned)n_cta);
         cfg.blockDim = dim3(pl->n_warps * 32);
-        kernel_fn fn = (!lengths && p.use_log && !p.out_fmask && p.preemph == 0.f) ? pick_fast_kernel(pl) : nullptr;
+        kernel_fn fn = (p.use_log && p.preemph == 0.f) ? pick_fast_kernel(pl, false, lengths || p.out_fmask) : nullptr;
         if (!fn) fn = pick_kernel(pl->pair, 0, true, pl->cfg.power, pl->top_groups, p.preemph != 0.f);
         le = cudaLaunchKernelEx(&cfg, fn, p);
         g_launches.fetch_add(1);

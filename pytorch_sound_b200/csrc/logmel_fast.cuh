@@ -26,18 +26,34 @@ constexpr int kFastSpan = 1024 + kFastHop;  // samples staged per task: two fram
 struct FastDesc {
     int b, t0;       // clip, first frame of the pair
     int delta;       // stage shift: sample s of the span sits at stage[s - s_first + delta]
-    unsigned flags;  // 2: frame t0 + 1 exists, 4: the span leaves [0, L) (reflect patch)
+    unsigned flags;  // 1: frame t0 exists (always, without `lengths`), 2: frame t0 + 1 exists, 4: the span leaves [0, Li) (reflect patch)
+    int Li;          // valid samples of the clip (kLen instantiations: lengths[b]; otherwise L)
 };
 
 // Locate a task and (lane 0) request its samples: one bulk copy of the in-range part of the 1280-sample span
 // (copy_geom in logmel_kernel.cuh: widened to 16-byte boundaries, clamped to the tensor).
+// kLen: per-clip `lengths` (zero-padded batches, SpeechDataLoader.pad_collate_fn): the clip ends at lengths[b], reflection
+// happens there, and a task whose first frame lies past the clip's last frame requests nothing.
+template <bool kLen = false>
 __device__ __forceinline__ FastDesc fast_request(const KParams &p, int b, int q, int lane, uint32_t stage_s, uint32_t bar) {
     FastDesc d;
     d.b = b;
     d.t0 = 2 * q;
-    const CopyGeom g = copy_geom(p, b, d.t0 * kFastHop - p.pad, kFastSpan, p.L);
+    d.Li = p.L;
+    int Ti = p.T;
+    if constexpr (kLen) {
+        if (p.lengths) {
+            d.Li = min(__ldg(p.lengths + b), p.L);
+            Ti = min(frames_of(d.Li, kFastSpan - kFastHop, kFastHop, p.pad), p.T);
+        }
+    }
+    if (kLen && d.t0 >= Ti) {
+        d.delta = 0, d.flags = 0;
+        return d;
+    }
+    const CopyGeom g = copy_geom(p, b, d.t0 * kFastHop - p.pad, kFastSpan, d.Li);
     d.delta = g.delta;
-    d.flags = (d.t0 + 1 < p.T ? 2u : 0u) | (g.patch ? 4u : 0u);
+    d.flags = 1u | (d.t0 + 1 < Ti ? 2u : 0u) | (g.patch ? 4u : 0u);
     if (lane == 0) issue_copy(g, stage_s, bar);
     return d;
 }
@@ -46,7 +62,7 @@ __device__ __forceinline__ FastDesc fast_request(const KParams &p, int b, int q,
 // even when it lies past the clip's last frame — on the reflected continuation — and simply not stored).
 __device__ __forceinline__ void fast_patch_halo(const KParams &p, const FastDesc &d, float *stage, int lane) {
     const int s_first = d.t0 * kFastHop - p.pad;
-    patch_stage(p, d.b, s_first, kFastSpan, p.L, copy_geom(p, d.b, s_first, kFastSpan, p.L), stage, lane);
+    patch_stage(p, d.b, s_first, kFastSpan, d.Li, copy_geom(p, d.b, s_first, kFastSpan, d.Li), stage, lane);
 }
 
 // stage -> registers with the generated periodic Hann applied: a[j] = {x_t[32 j + lane], x_t+1[32 j + lane]} * w[32 j + lane]
@@ -88,7 +104,8 @@ constexpr int kDctPitch = 64;  // floats per mel row of the shared DCT matrix: {
 // kDct: MelToMFCC / MFCC (models/transforms.py:419-455) fused as an epilogue — the lanes leave their log-mel values
 // of the two frames in a per-warp column, and lane c then forms coefficients c and 32 + c of both frames from the
 // shared DCT matrix (one broadcast 128-bit load of two column entries per four FFMA2).
-template <int kTop, unsigned kSig, int kPower, bool kDct = false>
+// kLen: per-clip `lengths` and / or the SpectrogramMasker frame mask (the data-path hook: GpuFeatureLoader passes both).
+template <int kTop, unsigned kSig, int kPower, bool kDct = false, bool kLen = false>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_fast_kernel(const KParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -141,10 +158,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_fast_kernel(const KP
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     FastDesc cur;
-    cur.b = cur.t0 = cur.delta = 0;
+    cur.b = cur.t0 = cur.delta = cur.Li = 0;
     cur.flags = 0;
     __syncwarp();
-    if (task < p.n_tasks) cur = fast_request(p, cb, cq, lane, stage_s, bar);
+    if (task < p.n_tasks) cur = fast_request<kLen>(p, cb, cq, lane, stage_s, bar);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int dct_rows = (p.n_mels + 1) & ~1;
     float *s_dct = reinterpret_cast<float *>(smem_raw + p.off_dct);
@@ -176,6 +193,18 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_fast_kernel(const KP
         if (cq >= p.tasks_per_clip) cq -= p.tasks_per_clip, ++cb;
         float2 a[32];
 
+        if constexpr (kLen) {
+            if (p.out_fmask && lane < 2 && d.t0 + lane < p.T)  // frame mask of this task's frames (models/transforms.py:397-416)
+                p.out_fmask[(long long)d.b * p.T + d.t0 + lane] = ((d.t0 + lane) * kFastHop - p.win_half < d.Li) ? 1.f : 0.f;
+            if (!(d.flags & 2u)) {   // frames past the clip's own end are zeros, as pad_collate_fn zero-pads per-item features
+                for (int tt = d.t0 + ((d.flags & 1u) ? 1 : 0); tt <= d.t0 + 1 && tt < p.T; ++tt)
+                    for (int m = lane; m < p.n_mels; m += 32) p.out_mel[((long long)d.b * p.n_mels + m) * (long long)p.T + tt] = 0.f;
+            }
+            if (!(d.flags & 1u)) {   // nothing was requested for this task
+                if (task + stride < p.n_tasks) cur = fast_request<kLen>(p, cb, cq, lane, stage_s, bar);
+                continue;
+            }
+        }
         mbar_wait(bar, parity);
         parity ^= 1;
         if (d.flags & 4u) fast_patch_halo(p, d, stage, lane);
@@ -191,7 +220,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) logmel_fast_kernel(const KP
         xpose_read_twiddle<B200MEL_XPOSE_BATCH>(a, buf, s_tw, lane);
         __syncwarp();  // transpose buffer is dead: magnitude tile and next stage may reuse it
 
-        if (task + stride < p.n_tasks) cur = fast_request(p, cb, cq, lane, stage_s, bar);
+        if (task + stride < p.n_tasks) cur = fast_request<kLen>(p, cb, cq, lane, stage_s, bar);
 
         int2 ents[kRounds];  // {lo, m} of every mel round, fetched here so the latency hides under pass 2
 #pragma unroll

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kGroups * SpecShape<kPair>::kGW * 32, 1) spec_
         reinterpret_cast<int4 *>(s_win)[i] = __ldg(reinterpret_cast<const int4 *>(p.window) + i);
     asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: caller memory is only touched below this line
     FastDesc cur;
-    cur.b = cur.t0 = cur.delta = 0;
+    cur.b = cur.t0 = cur.delta = cur.Li = 0;
     cur.flags = 0;
     if constexpr (kFast) {
         __syncwarp();
